@@ -1,0 +1,125 @@
+/* libsmnngp - C-ABI of the B200 (sm_100a) NNGP exact-GP hot path.
+ *
+ * Drop-in boundary for the reference's spax kernel / model / likelihood API
+ * (Hyungi-Lee/Scale-Mixtures-of-Neural-Network-Gaussian-Processes).  Every entry point below replaces work the
+ * reference delegates to neural_tangents / jax.lax.linalg behind the cited call site.  Conventions:
+ *   - all matrices row-major FP64; every pointer is a DEVICE pointer unless the function name ends in _host_f64;
+ *   - `stream` is a cudaStream_t passed as void*; functions only enqueue (no host sync, no allocation), so they
+ *     are CUDA-graph capturable; the *_host_f64 variants allocate / copy / synchronise themselves;
+ *   - `hp_dev` is a device array of 6 doubles {w_std, b_std, last_w_std, eps, alpha, beta} - the softplus'ed
+ *     "safe values" of the six trainable scalars (spax/kernels.py:19-21, spax/models.py:91,
+ *     spax/likelihoods.py:42-43).  They are runtime operands (traced in the reference), never baked in;
+ *   - return value: 0 = ok, non-zero = invalid argument / CUDA error (text via smnngp_last_error()).  A
+ *     non-positive-definite matrix is NOT an error: outputs are NaN and *info_dev = 1 + index of the first bad
+ *     pivot, mirroring jax's lax.linalg.cholesky NaN semantics that regression/train.py:211 relies on;
+ *   - workspaces are caller-owned (so the framework allocator accounts for them): ask *_workspace_bytes first.
+ */
+#ifndef SMNNGP_H_
+#define SMNNGP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMNNGP_ABI_VERSION 1
+
+enum { SMNNGP_OK = 0, SMNNGP_EINVAL = 1, SMNNGP_ECUDA = 2, SMNNGP_EWORKSPACE = 3 };
+/* experiments/nt_kernels.py:12-18 get_act_class */
+enum { SMNNGP_ACT_RELU = 0, SMNNGP_ACT_ERF = 1 };
+/* experiments/nt_kernels.py:21 get_mlp_kernel, :83 get_dense_resnet_kernel */
+enum { SMNNGP_ARCH_MLP = 0, SMNNGP_ARCH_RESNET = 1 };
+/* spax/likelihoods.py:22 GaussianLikelihood, :37 StudentTLikelihood */
+enum { SMNNGP_KIND_GAUSS = 0, SMNNGP_KIND_STUDENT_T = 1 };
+/* diagonal regulariser folded into the Gram epilogue:
+ *   EPS_ABS  K + eps I                (spax/models.py:96 + spax/utils.py:26-27 jitter)
+ *   EPS_REL  K + eps tr(K)/N I        (neural_tangents predict diag_reg, spax/kernels.py:30)
+ *   LIK      K + 1e-6 (alpha/beta) I  (spax/likelihoods.py:60, after factoring out beta/alpha) */
+enum { SMNNGP_SHIFT_NONE = 0, SMNNGP_SHIFT_EPS_ABS = 1, SMNNGP_SHIFT_EPS_REL = 2, SMNNGP_SHIFT_LIK = 3 };
+enum { SMNNGP_OUT_FULL = 0, SMNNGP_OUT_LOWER = 1 };
+
+int smnngp_abi_version(void);
+const char* smnngp_last_error(void);
+
+/* ---- Gram: replaces kernel_fn(x1, x2, get="nngp") of spax/kernels.py:23-27 with the layer stacks of
+ * experiments/nt_kernels.py:21-31 / :83-103.  X2 == NULL (or == X) selects the symmetric path: only tiles on or
+ * below the diagonal are computed; out_mode FULL mirrors them, LOWER leaves the strict upper part untouched.
+ * `shift` is only honoured on the symmetric path. */
+size_t smnngp_gram_workspace_bytes(int64_t N, int64_t M, int n_hidden, int arch);
+int smnngp_gram_f64(void* stream, const double* X, const double* X2, int64_t N, int64_t M, int64_t D,
+                    int n_hidden, int act, int arch, const double* hp_dev, int shift, int out_mode,
+                    double* K_out, int64_t ld, void* workspace, size_t workspace_bytes);
+/* marginal variances k(x_i, x_i) of the same stack (the diagonal NT carries as cov1) */
+int smnngp_nngp_diag_f64(void* stream, const double* X, int64_t N, int64_t D, int n_hidden, int act, int arch,
+                         const double* hp_dev, double* q_out, void* workspace, size_t workspace_bytes);
+
+/* ---- Cholesky: replaces lax.linalg.cholesky (spax/utils.py:179).  In place on the lower triangle of the
+ * row-major A; the strict upper triangle is neither read nor written.  The trapezoid form factors the leading
+ * N x N of A [M, N] (M >= N) and turns the extra rows R into R L^-T, i.e. it also performs the triangular
+ * solves of spax/utils.py:180 / cho_solve for right-hand sides appended as rows.
+ * *logdet_dev receives sum_i log L_ii. */
+size_t smnngp_potrf_workspace_bytes(int64_t N);
+int smnngp_potrf_f64(void* stream, double* A, int64_t N, int64_t ld, int* info_dev, void* workspace,
+                     size_t workspace_bytes);
+int smnngp_potrf_trapezoid_f64(void* stream, double* A, int64_t M, int64_t N, int64_t ld, double* logdet_dev,
+                               int* info_dev, void* workspace, size_t workspace_bytes);
+
+/* ---- generic covariance solve: factors (scale * cov + shift I) in workspace (cov is not modified) and returns
+ * out_dev[2] = { sum_i log L_ii, ||L^-1 y||^2 }.  Backs Likelihood.prior_logpdf(y, cov)
+ * (spax/likelihoods.py:25-28, :45-50) and the `d` term of StudentTLikelihood.logpdf (:60-61) when the caller
+ * passes an explicit covariance instead of using the fused entry points.  N < 65535. */
+size_t smnngp_cov_solve_workspace_bytes(int64_t N);
+int smnngp_cov_solve_f64(void* stream, const double* cov, int64_t N, int64_t ld, const double* y, double scale,
+                         double shift, void* workspace, size_t workspace_bytes, double* out_dev, int* info_dev);
+
+/* ---- fused log marginal likelihood: replaces SPR.loss (spax/models.py:93-98) =
+ * Gram + jitter + prior_logpdf (spax/likelihoods.py:25-28 / :45-50 -> spax/utils.py:160-183).
+ * out_dev[4] = { log p(y), -log p(y)/N (the loss), sum_i log L_ii of chol(K + eps I), ||L^-1 y||^2 }.
+ * The N x N matrix lives only in `workspace`. */
+size_t smnngp_lml_workspace_bytes(int64_t N, int64_t D, int n_hidden, int arch);
+int smnngp_lml_f64(void* stream, const double* X, const double* y, int64_t N, int64_t D, int n_hidden, int act,
+                   int arch, const double* hp_dev, int kind, void* workspace, size_t workspace_bytes,
+                   double* out_dev, int* info_dev);
+
+/* ---- predictive: replaces NNGPKernel.predict (spax/kernels.py:29-32 -> neural_tangents
+ * gradient_descent_mse_ensemble, get="nngp", compute_cov=True) with `shift` = EPS_REL.  Y is [N, C];
+ * mean_out [T, C]; var_out [T] = diag(cov) - the only part of cov the reference consumes
+ * (spax/likelihoods.py:31, :62). */
+size_t smnngp_predict_workspace_bytes(int64_t N, int64_t T, int64_t C, int64_t D, int n_hidden, int arch);
+int smnngp_predict_f64(void* stream, const double* X, const double* Y, const double* Xt, int64_t N, int64_t T,
+                       int64_t C, int64_t D, int n_hidden, int act, int arch, const double* hp_dev, int shift,
+                       void* workspace, size_t workspace_bytes, double* mean_out, double* var_out,
+                       int* info_dev);
+
+/* ---- SPR.test_nll (spax/models.py:100-120) incl. Likelihood.logpdf (spax/likelihoods.py:30-33 / :52-65):
+ * predictive (relative jitter) + second factorisation of K + 1e-6 (alpha/beta) I for the Student-t scale +
+ * de-standardisation + mean negative log density.  nll_out_dev[1]; mean_out / var_out / logp_out are [T] and
+ * may be NULL.  workspace: smnngp_predict_workspace_bytes(N, T, 1, D, ...). */
+int smnngp_test_nll_f64(void* stream, const double* X, const double* y, const double* Xt, const double* yt,
+                        int64_t N, int64_t T, int64_t D, int n_hidden, int act, int arch, const double* hp_dev,
+                        int kind, double y_mean, double y_std, void* workspace, size_t workspace_bytes,
+                        double* nll_out_dev, double* mean_out, double* var_out, double* logp_out,
+                        int* info_dev);
+
+/* ---- host-buffer entry points (what a ctypes / cgo / JNI caller without device arrays binds): inputs and
+ * outputs are HOST pointers; device staging comes from a grow-only arena released by smnngp_host_release(). */
+int smnngp_lml_host_f64(const double* X, const double* y, int64_t N, int64_t D, int n_hidden, int act, int arch,
+                        const double* hp, int kind, double* out, int* info);
+int smnngp_predict_host_f64(const double* X, const double* Y, const double* Xt, int64_t N, int64_t T, int64_t C,
+                            int64_t D, int n_hidden, int act, int arch, const double* hp, int shift,
+                            double* mean_out, double* var_out, int* info);
+int smnngp_test_nll_host_f64(const double* X, const double* y, const double* Xt, const double* yt, int64_t N,
+                             int64_t T, int64_t D, int n_hidden, int act, int arch, const double* hp, int kind,
+                             double y_mean, double y_std, double* nll_out, double* mean_out, double* var_out,
+                             int* info);
+void smnngp_host_release(void);
+
+/* tuning knob: outer panel width of the Cholesky (multiple of 128; 0 = automatic) */
+void smnngp_set_panel_width(int nb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMNNGP_H_ */

@@ -1,0 +1,136 @@
+"""ctypes binding of libsmnngp.so (C-ABI declared in include/smnngp.h) + the in-tree nvcc build.
+
+There is no CPU fallback: if the library cannot be built / loaded every op raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_DIR = os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libsmnngp.so")
+SOURCES = ["gram.cu", "chol.cu", "reduce.cu", "api.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets"]
+
+EXPORTS = [
+    "smnngp_abi_version", "smnngp_last_error", "smnngp_gram_workspace_bytes", "smnngp_gram_f64",
+    "smnngp_nngp_diag_f64", "smnngp_potrf_workspace_bytes", "smnngp_potrf_f64", "smnngp_potrf_trapezoid_f64",
+    "smnngp_cov_solve_workspace_bytes", "smnngp_cov_solve_f64",
+    "smnngp_lml_workspace_bytes", "smnngp_lml_f64", "smnngp_predict_workspace_bytes", "smnngp_predict_f64",
+    "smnngp_test_nll_f64", "smnngp_lml_host_f64", "smnngp_predict_host_f64", "smnngp_test_nll_host_f64",
+    "smnngp_host_release", "smnngp_set_panel_width",
+]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: cannot build libsmnngp.so (no CPU fallback exists)")
+    return exe
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "smnngp.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into lib/libsmnngp.so (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = _nvcc()
+    os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = os.path.join(_HERE, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+
+    def cc(src):
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(cc, SOURCES))
+    r = subprocess.run([nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB_PATH
+
+
+_lib = None
+
+_vp, _i64, _i, _d, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_size_t
+
+
+def _declare(lib):
+    lib.smnngp_abi_version.restype = _i
+    lib.smnngp_last_error.restype = C.c_char_p
+    lib.smnngp_gram_workspace_bytes.restype = _sz
+    lib.smnngp_gram_workspace_bytes.argtypes = [_i64, _i64, _i, _i]
+    lib.smnngp_gram_f64.argtypes = [_vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _i, _vp, _i64, _vp, _sz]
+    lib.smnngp_nngp_diag_f64.argtypes = [_vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp, _vp, _sz]
+    lib.smnngp_potrf_workspace_bytes.restype = _sz
+    lib.smnngp_potrf_workspace_bytes.argtypes = [_i64]
+    lib.smnngp_potrf_f64.argtypes = [_vp, _vp, _i64, _i64, _vp, _vp, _sz]
+    lib.smnngp_potrf_trapezoid_f64.argtypes = [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _sz]
+    lib.smnngp_cov_solve_workspace_bytes.restype = _sz
+    lib.smnngp_cov_solve_workspace_bytes.argtypes = [_i64]
+    lib.smnngp_cov_solve_f64.argtypes = [_vp, _vp, _i64, _i64, _vp, _d, _d, _vp, _sz, _vp, _vp]
+    lib.smnngp_lml_workspace_bytes.restype = _sz
+    lib.smnngp_lml_workspace_bytes.argtypes = [_i64, _i64, _i, _i]
+    lib.smnngp_lml_f64.argtypes = [_vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _i, _vp, _sz, _vp, _vp]
+    lib.smnngp_predict_workspace_bytes.restype = _sz
+    lib.smnngp_predict_workspace_bytes.argtypes = [_i64, _i64, _i64, _i64, _i, _i]
+    lib.smnngp_predict_f64.argtypes = [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _vp, _sz,
+                                       _vp, _vp, _vp]
+    lib.smnngp_test_nll_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _d, _d,
+                                        _vp, _sz, _vp, _vp, _vp, _vp, _vp]
+    lib.smnngp_lml_host_f64.argtypes = [_vp, _vp, _i64, _i64, _i, _i, _i, _vp, _i, _vp, _vp]
+    lib.smnngp_predict_host_f64.argtypes = [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _vp, _vp,
+                                            _vp]
+    lib.smnngp_test_nll_host_f64.argtypes = [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _d, _d,
+                                             _vp, _vp, _vp, _vp]
+    lib.smnngp_host_release.restype = None
+    lib.smnngp_set_panel_width.restype = None
+    lib.smnngp_set_panel_width.argtypes = [_i]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("smnngp_abi_version",):
+            fn.restype = _i
+
+
+def load():
+    """Return the loaded library; builds it on first use when the .so is missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = LIB_PATH
+    if _stale():
+        path = build()
+    lib = C.CDLL(path)
+    _declare(lib)
+    if lib.smnngp_abi_version() != 1:
+        raise RuntimeError("libsmnngp.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().smnngp_last_error().decode()
+        raise RuntimeError(f"libsmnngp {what} failed (status {rc}): {msg}")

@@ -1,0 +1,227 @@
+// NNGP Gram matrix for the MLP / dense-resnet stacks of the reference (experiments/nt_kernels.py:21-31,
+// :83-103, called through spax/kernels.py:23-27): one FP64 tensor-core X.X'^T contraction whose epilogue
+// applies the whole L-layer ReLU arc-cosine / erf recursion in registers, so every kernel entry is written to
+// HBM exactly once.  Symmetric case: only tiles on or below the diagonal are computed (optionally mirrored).
+#include "gemm_core.cuh"
+#include "kernels.cuh"
+
+namespace smnngp {
+
+namespace {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kInv2Pi = 0.15915494309189533577;
+constexpr double kTwoOverPi = 0.63661977236758134308;
+
+__device__ __forceinline__ double act_diag(double u, int act) {
+  if (act == ACT_RELU) return 0.5 * u;
+  return kTwoOverPi * asin(2.0 * u / (1.0 + 2.0 * u));
+}
+// what the Gram epilogue needs per row and layer: relu -> u itself, erf -> 1/sqrt(1+2u)
+__device__ __forceinline__ double encode_var(double u, int act) {
+  return act == ACT_RELU ? u : 1.0 / sqrt(1.0 + 2.0 * u);
+}
+
+// one nonlinearity on a cross-covariance k given the encoded marginals of its row and column
+template <int ACT>
+__device__ __forceinline__ double phi(double k, double t1, double t2) {
+  if (ACT == ACT_RELU) {
+    double s = sqrt(fmax(__dsub_rn(__dmul_rn(t1, t2), __dmul_rn(k, k)), 0.0));
+    double th = (s == 0.0 && k == 0.0) ? 0.5 * kPi : atan2(s, k);
+    return s * kInv2Pi + (0.5 - th * kInv2Pi) * k;
+  } else {
+    double x = 2.0 * k * t1 * t2;
+    x = fmin(fmax(x, -1.0), 1.0);
+    return kTwoOverPi * asin(x);
+  }
+}
+
+__global__ void qtable_kernel(const double* __restrict__ X, long long ldx, int N, int D, int n_hidden, int act,
+                              int arch, const double* __restrict__ hp, double* __restrict__ tab,
+                              long long tab_ld, double* __restrict__ qfin) {
+  int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const double* x = X + (long long)row * ldx;
+  double s = 0.0;
+  for (int k = lane; k < D; k += 32) s = fma(x[k], x[k], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane != 0) return;
+  const double w2 = hp[HP_W] * hp[HP_W], b2 = hp[HP_B] * hp[HP_B], v2 = hp[HP_V] * hp[HP_V];
+  double q = s / (double)D;
+  if (arch == ARCH_MLP) {
+    for (int a = 0; a < n_hidden; a++) {
+      double u = w2 * q + b2;
+      tab[a * tab_ld + row] = encode_var(u, act);
+      q = act_diag(u, act);
+    }
+  } else {
+    double u = w2 * q + b2;
+    for (int a = 0; a < n_hidden; a++) {
+      tab[a * tab_ld + row] = encode_var(u, act);
+      u = u + (w2 * act_diag(u, act) + b2);
+    }
+    tab[(long long)n_hidden * tab_ld + row] = encode_var(u, act);
+    q = act_diag(u, act);
+  }
+  qfin[row] = v2 * q;
+}
+
+// single block, fixed reduction order (deterministic)
+__global__ void scalars_kernel(const double* __restrict__ qfin, int N, const double* __restrict__ hp,
+                               double* __restrict__ scal) {
+  __shared__ double red[1024];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += qfin[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double trmean = red[0] / (double)N;
+    double eps = hp[HP_EPS];
+    scal[SC_TRMEAN] = trmean;
+    scal[SC_SHIFT0 + SHIFT_NONE] = 0.0;
+    scal[SC_SHIFT0 + SHIFT_EPS_ABS] = eps;
+    scal[SC_SHIFT0 + SHIFT_EPS_REL] = eps * trmean;
+    scal[SC_SHIFT0 + SHIFT_LIK] = 1e-6 * hp[HP_ALPHA] / hp[HP_BETA];
+    scal[SC_LOGDET] = 0.0;
+    scal[SC_QUAD] = 0.0;
+  }
+}
+
+template <bool ALIGN16, int ACT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gram_kernel(const GramParams p) {
+  extern __shared__ __align__(16) double smem[];
+  const int ntn = (p.M + BN - 1) / BN;
+  int ti, tj;
+  decode_tile(blockIdx.x, ntn, p.symmetric, ti, tj);
+  const int r0 = ti * BM, c0 = tj * BN;
+  double acc[MI][NI][2];
+  gemm_mainloop<ALIGN16>(acc, p.X1 + (long long)r0 * p.ld1, p.ld1, min(BM, p.N - r0),
+                         p.X2 + (long long)c0 * p.ld2, p.ld2, min(BN, p.M - c0), p.D, smem);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rbase = r0 + (warp >> 2) * 64 + (lane >> 2);
+  const int cbase = c0 + (warp & 3) * 32 + (lane & 3) * 2;
+  const double w2 = p.hp[HP_W] * p.hp[HP_W], b2 = p.hp[HP_B] * p.hp[HP_B], v2 = p.hp[HP_V] * p.hp[HP_V];
+  const bool diag_tile = p.symmetric && (ti == tj);
+  const double dD = (double)p.D;
+  const bool resnet = p.arch == ARCH_RESNET;
+
+  // which of this thread's 64 entries are real output (edge tiles, strict upper part of diagonal tiles)
+  unsigned long long live = 0ull;
+#pragma unroll
+  for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int r = rbase + mi * 8, c = cbase + ni * 8 + e;
+        bool ok = r < p.N && c < p.M && (!diag_tile || c <= r);
+        if (ok) live |= 1ull << (mi * 8 + ni * 2 + e);
+        double k = acc[mi][ni][e] / dD;                 // kernel_fn normalises X.X'^T by the feature count
+        acc[mi][ni][e] = resnet ? (w2 * k + b2) : k;    // dense-resnet: leading Dense(512)
+      }
+
+  const int n_act = resnet ? p.n_hidden + 1 : p.n_hidden;
+  for (int a = 0; a < n_act; a++) {
+    double tr[MI], tc[NI][2];
+#pragma unroll
+    for (int mi = 0; mi < MI; mi++) {
+      int r = rbase + mi * 8;
+      tr[mi] = r < p.N ? p.tab1[a * p.tab_ld1 + r] : 1.0;
+    }
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int c = cbase + ni * 8 + e;
+        tc[ni][e] = c < p.M ? p.tab2[a * p.tab_ld2 + c] : 1.0;
+      }
+    const bool plain = !resnet || (a == n_act - 1);     // MLP layer, or the trailing activation of the resnet
+#pragma unroll
+    for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+      for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          if (!((live >> (mi * 8 + ni * 2 + e)) & 1ull)) continue;
+          double k = acc[mi][ni][e];
+          if (!resnet) k = w2 * k + b2;                 // Dense(512, W_std, b_std)
+          double ph = phi<ACT>(k, tr[mi], tc[ni][e]);
+          acc[mi][ni][e] = plain ? ph : k + (w2 * ph + b2);  // ResBlock: z + Dense(act(z))
+        }
+  }
+
+  const double sh = (p.symmetric && p.shift != SHIFT_NONE) ? p.scal[SC_SHIFT0 + p.shift] : 0.0;
+  const bool vec_ok = ((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15) == 0);
+  const bool mirror = p.symmetric && p.out_full && !diag_tile;
+#pragma unroll
+  for (int mi = 0; mi < MI; mi++) {
+    const int r = rbase + mi * 8;
+    if (r >= p.N) continue;
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++) {
+      const int c = cbase + ni * 8;
+      double k0 = v2 * acc[mi][ni][0], k1 = v2 * acc[mi][ni][1];   // final Dense(num_class, W_std=last_w_std)
+      if (p.symmetric) {
+        if (r == c) k0 += sh;
+        if (r == c + 1) k1 += sh;
+      }
+      const bool ok0 = (live >> (mi * 8 + ni * 2)) & 1ull, ok1 = (live >> (mi * 8 + ni * 2 + 1)) & 1ull;
+      double* dst = p.K + (long long)r * p.ldk + c;
+      if (ok0 && ok1 && vec_ok) {
+        *reinterpret_cast<double2*>(dst) = make_double2(k0, k1);
+      } else {
+        if (ok0) dst[0] = k0;
+        if (ok1) dst[1] = k1;
+      }
+      if (mirror) {
+        if (ok0) p.K[(long long)c * p.ldk + r] = k0;
+        if (ok1) p.K[(long long)(c + 1) * p.ldk + r] = k1;
+      } else if (diag_tile && p.out_full) {
+        if (ok0 && c != r) p.K[(long long)c * p.ldk + r] = k0;
+        if (ok1 && c + 1 != r) p.K[(long long)(c + 1) * p.ldk + r] = k1;
+      }
+    }
+  }
+}
+
+template <bool ALIGN16>
+cudaError_t launch_gram_t(cudaStream_t s, const GramParams& p, long long tiles) {
+  auto kern = p.act == ACT_RELU ? gram_kernel<ALIGN16, ACT_RELU> : gram_kernel<ALIGN16, ACT_ERF>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)tiles, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_qtable(cudaStream_t s, const double* X, long long ldx, int N, int D, int n_hidden, int act,
+                          int arch, const double* hp, double* tab, long long tab_ld, double* qfin) {
+  if (N <= 0) return cudaSuccess;
+  int warps_per_block = 8;
+  unsigned blocks = (unsigned)((N + warps_per_block - 1) / warps_per_block);
+  qtable_kernel<<<blocks, warps_per_block * 32, 0, s>>>(X, ldx, N, D, n_hidden, act, arch, hp, tab, tab_ld, qfin);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scalars(cudaStream_t s, const double* qfin, int N, const double* hp, double* scal) {
+  scalars_kernel<<<1, 1024, 0, s>>>(qfin, N, hp, scal);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gram(cudaStream_t s, const GramParams& p) {
+  if (p.N <= 0 || p.M <= 0) return cudaSuccess;
+  long long tiles = count_tiles(p.N, p.M, p.symmetric);
+  bool a16 = (p.ld1 % 2 == 0) && (p.ld2 % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.X1) & 15) == 0) &&
+             ((reinterpret_cast<uintptr_t>(p.X2) & 15) == 0);
+  return a16 ? launch_gram_t<true>(s, p, tiles) : launch_gram_t<false>(s, p, tiles);
+}
+
+}  // namespace smnngp

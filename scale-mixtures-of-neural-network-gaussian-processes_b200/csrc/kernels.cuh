@@ -1,0 +1,76 @@
+// Internal (C++) launch interface of libsmnngp: every function only enqueues work on `stream`.
+#pragma once
+#include "common.cuh"
+
+namespace smnngp {
+
+constexpr int HP_W = 0, HP_B = 1, HP_V = 2, HP_EPS = 3, HP_ALPHA = 4, HP_BETA = 5, HP_COUNT = 6;
+constexpr int PB = 128;  // diagonal block / inner panel width of the Cholesky
+
+inline int n_act_applications(int n_hidden, int arch) { return arch == ARCH_RESNET ? n_hidden + 1 : n_hidden; }
+
+struct GramParams {
+  const double* X1;   // [N, D] rows of the output
+  const double* X2;   // [M, D] cols of the output (== X1 for the symmetric case)
+  long long ld1, ld2;
+  int N, M, D;
+  const double* tab1; // [n_act, tab_ld1] per-layer encoded marginal variances of X1 rows
+  const double* tab2;
+  long long tab_ld1, tab_ld2;
+  int n_hidden, act, arch;
+  const double* hp;   // device: w_std, b_std, last_w_std, ...
+  const double* scal; // device scalar block (diagonal shift values)
+  int shift;          // enum Shift, applied where global row == global col (symmetric only)
+  int symmetric;      // 1: only tiles tj <= ti are computed
+  int out_full;       // symmetric only: also store the mirrored element
+  double* K;
+  long long ldk;
+};
+
+struct GemmParams {
+  const double* A;    // [M, K] rows
+  const double* B;    // [N, K] rows
+  double* C;          // [M, N]
+  long long lda, ldb, ldc;
+  int M, N, K;
+  int lower;          // 1: C(0,0) is on the diagonal; only elements col <= row are touched
+};
+
+// ---- NNGP Gram -------------------------------------------------------------------------------------------
+// per-row layer table + final marginal variance (nngp diag) for X [N, D]
+cudaError_t launch_qtable(cudaStream_t s, const double* X, long long ldx, int N, int D, int n_hidden, int act,
+                          int arch, const double* hp, double* tab, long long tab_ld, double* qfin);
+// scal[SC_TRMEAN], shift table; zeroes the log-det / quad accumulators
+cudaError_t launch_scalars(cudaStream_t s, const double* qfin, int N, const double* hp, double* scal);
+cudaError_t launch_gram(cudaStream_t s, const GramParams& p);
+
+// ---- Cholesky --------------------------------------------------------------------------------------------
+// Factor the w x w (w <= 128) diagonal block at A (row-major, lower) in place, write inv(L) (128x128, ld 128,
+// zero above the diagonal, identity padded) to Linv, add sum(log L_ii) to *logdet, record first bad pivot.
+cudaError_t launch_potf2_trtri(cudaStream_t s, double* A, long long lda, int w, double* Linv, double* logdet,
+                               int* info, int global_col0);
+// C = A * B^T (store) or C -= A * B^T (lower-masked when p.lower)
+cudaError_t launch_gemm_store(cudaStream_t s, const GemmParams& p);
+cudaError_t launch_gemm_sub(cudaStream_t s, const GemmParams& p);
+// Blocked right-looking Cholesky of the leading N x N of the row-major trapezoid A [Mtot, N] (lower part);
+// rows N..Mtot-1 are carried along and end up as (rows) * L^-T.  NB = outer panel (multiple of 128).
+cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long Mtot, long long N, int NB,
+                            double* Linv_ws, double* logdet, int* info);
+
+// ---- reductions / closed forms ---------------------------------------------------------------------------
+cudaError_t launch_sumsq(cudaStream_t s, const double* z, long long n, double* out);
+// out[0] = lml, out[1] = -lml/N (SPR.loss), out[2] = sum log L_ii (of K + shift I), out[3] = ||L^-1 y||^2
+cudaError_t launch_lml_finalize(cudaStream_t s, const double* scal, const double* hp, int kind, long long N,
+                                const int* info, double* out);
+// V [T, ldv] = K_td L^-T rows, Z [C, ldz] = (L^-1 Y)^T rows, ktt [T] prior variances
+cudaError_t launch_predict_finalize(cudaStream_t s, const double* V, long long ldv, const double* Z,
+                                    long long ldz, const double* ktt, int T, int C, long long N,
+                                    const int* info, double* mean, double* var);
+// SPR.test_nll tail: per-test log-density and its mean.  scal2 holds ||L2^-1 y||^2 for the Student-t d term.
+cudaError_t launch_test_nll_finalize(cudaStream_t s, const double* mean, const double* var, const double* ytest,
+                                     int T, long long N, double y_mean, double y_std, const double* hp,
+                                     int kind, const double* quad2, const int* info, double* logp,
+                                     double* nll_out);
+cudaError_t launch_fill_nan_if_bad(cudaStream_t s, const int* info, double* buf, long long n);
+
+}  // namespace smnngp

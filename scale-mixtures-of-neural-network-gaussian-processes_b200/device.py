@@ -1,0 +1,274 @@
+"""Device-level ops: thin, allocation-aware wrappers over the C-ABI (include/smnngp.h).
+
+PyTorch is used for device memory and streams only.  Inputs may be torch CUDA tensors (device entry points,
+enqueue-only on the current stream) or NumPy arrays (host entry points: copies included, synchronous).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ACT = {"relu": 0, "erf": 1}
+ARCH = {"mlp": 0, "resnet": 1}
+KIND = {"gauss": 0, "student_t": 1}
+SHIFT = {"none": 0, "eps_abs": 1, "eps_rel": 2, "lik": 3}
+
+
+@dataclass(frozen=True)
+class StackSpec:
+    """The layer stack of experiments/nt_kernels.py:21-31 (mlp) / :83-103 (resnet)."""
+    num_hiddens: int
+    act: str = "relu"
+    arch: str = "mlp"
+
+    def ids(self):
+        if self.act not in ACT:
+            raise KeyError("Unsupported act '{}'".format(self.act))      # nt_kernels.py:18
+        if self.arch not in ARCH:
+            raise ValueError(f"Unsupported network '{self.arch}'")       # regression/train.py:124
+        return int(self.num_hiddens), ACT[self.act], ARCH[self.arch]
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("smnngp: no CUDA device - this path has no CPU fallback")
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (torch.device(device).index or 0)
+    cur = _ws_cache.get(key)
+    if cur is None or cur.numel() < nbytes:
+        _ws_cache[key] = None
+        cur = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _ws_cache[key] = cur
+    return cur
+
+
+def release_workspaces():
+    _ws_cache.clear()
+    _lib.load().smnngp_host_release()
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _f64(x, device=None):
+    t = torch.as_tensor(x, dtype=torch.float64, device=device) if not isinstance(x, torch.Tensor) else x
+    if t.dtype != torch.float64:
+        t = t.to(torch.float64)
+    return t.contiguous()
+
+
+def make_hp(w_std, b_std, last_w_std, eps=1e-6, alpha=2.0, beta=2.0, device="cuda"):
+    """Device operand {w_std, b_std, last_w_std, eps, alpha, beta} (safe values)."""
+    vals = [float(v) for v in (w_std, b_std, last_w_std, eps, alpha, beta)]
+    return torch.tensor(vals, dtype=torch.float64, device=device)
+
+
+def _np_hp(w_std, b_std, last_w_std, eps=1e-6, alpha=2.0, beta=2.0):
+    return np.ascontiguousarray([w_std, b_std, last_w_std, eps, alpha, beta], dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def gram(x, x2=None, *, spec: StackSpec, hp, shift="none", lower_only=False, out=None):
+    """K = kernel_fn(x, x2, get="nngp") (spax/kernels.py:23-27).  Device tensors in, device tensor out."""
+    _require_cuda()
+    lib = _lib.load()
+    nh, act, arch = spec.ids()
+    x = _f64(x)
+    sym = x2 is None or x2 is x
+    x2t = None if sym else _f64(x2, x.device)
+    n, d = x.shape
+    m = n if sym else x2t.shape[0]
+    if not sym and x2t.shape[1] != d:
+        raise ValueError("feature dimensions differ")
+    if out is None:
+        out = torch.empty((n, m), dtype=torch.float64, device=x.device)
+        if lower_only:
+            out.zero_()
+    ws_bytes = lib.smnngp_gram_workspace_bytes(n, m, nh, arch)
+    ws = _workspace(ws_bytes, x.device)
+    rc = lib.smnngp_gram_f64(_stream(x.device), _p(x), _p(x2t), n, m, d, nh, act, arch, _p(hp), SHIFT[shift],
+                             1 if lower_only else 0, _p(out), out.stride(0), _p(ws), ws_bytes)
+    _lib.check(rc, "gram")
+    return out
+
+
+def nngp_diag(x, *, spec: StackSpec, hp):
+    _require_cuda()
+    lib = _lib.load()
+    nh, act, arch = spec.ids()
+    x = _f64(x)
+    n, d = x.shape
+    q = torch.empty(n, dtype=torch.float64, device=x.device)
+    ws_bytes = lib.smnngp_gram_workspace_bytes(n, n, nh, arch)
+    ws = _workspace(ws_bytes, x.device)
+    _lib.check(lib.smnngp_nngp_diag_f64(_stream(x.device), _p(x), n, d, nh, act, arch, _p(hp), _p(q), _p(ws),
+                                        ws_bytes), "nngp_diag")
+    return q
+
+
+def potrf_(a: torch.Tensor, n_cols=None):
+    """In-place lower Cholesky of the leading n_cols x n_cols of the row-major a [M, >=n_cols]; extra rows become
+    rows * L^-T.  Returns (sum log L_ii [device scalar], info [device int])."""
+    _require_cuda()
+    lib = _lib.load()
+    assert a.dtype == torch.float64 and a.is_cuda and a.stride(1) == 1
+    m = a.shape[0]
+    n = a.shape[1] if n_cols is None else n_cols
+    info = torch.zeros(1, dtype=torch.int32, device=a.device)
+    logdet = torch.zeros(1, dtype=torch.float64, device=a.device)
+    ws_bytes = lib.smnngp_potrf_workspace_bytes(n)
+    ws = _workspace(ws_bytes, a.device)
+    rc = lib.smnngp_potrf_trapezoid_f64(_stream(a.device), _p(a), m, n, a.stride(0), _p(logdet), _p(info), _p(ws),
+                                        ws_bytes)
+    _lib.check(rc, "potrf")
+    return logdet, info
+
+
+def cov_solve(cov, y, *, scale=1.0, shift=0.0):
+    """(sum log L_ii, ||L^-1 y||^2, info) for L = chol(scale * cov + shift I); cov is left untouched."""
+    _require_cuda()
+    lib = _lib.load()
+    cov = _f64(cov)
+    y = _f64(y, cov.device)
+    n = cov.shape[0]
+    out = torch.empty(2, dtype=torch.float64, device=cov.device)
+    info = torch.zeros(1, dtype=torch.int32, device=cov.device)
+    ws_bytes = lib.smnngp_cov_solve_workspace_bytes(n)
+    ws = _workspace(ws_bytes, cov.device)
+    rc = lib.smnngp_cov_solve_f64(_stream(cov.device), _p(cov), n, cov.stride(0), _p(y), float(scale), float(shift),
+                                  _p(ws), ws_bytes, _p(out), _p(info))
+    _lib.check(rc, "cov_solve")
+    return out[0], out[1], info
+
+
+def lml(x, y, *, spec: StackSpec, hp, kind="student_t"):
+    """Fused SPR.loss pieces (spax/models.py:93-98).  Device inputs -> (out[4] device tensor, info);
+    NumPy inputs -> host entry point, returns (np.ndarray[4], int).
+    out = [log p(y), -log p(y)/N, sum log L_ii, ||L^-1 y||^2]."""
+    lib = _lib.load()
+    nh, act, arch = spec.ids()
+    if isinstance(x, np.ndarray):
+        _require_cuda()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        hp = np.ascontiguousarray(hp, dtype=np.float64)
+        out = np.empty(4, dtype=np.float64)
+        info = C.c_int(0)
+        rc = lib.smnngp_lml_host_f64(x.ctypes.data, y.ctypes.data, x.shape[0], x.shape[1], nh, act, arch,
+                                     hp.ctypes.data, KIND[kind], out.ctypes.data, C.byref(info))
+        _lib.check(rc, "lml_host")
+        return out, info.value
+    _require_cuda()
+    x = _f64(x)
+    y = _f64(y, x.device)
+    n, d = x.shape
+    out = torch.empty(4, dtype=torch.float64, device=x.device)
+    info = torch.zeros(1, dtype=torch.int32, device=x.device)
+    ws_bytes = lib.smnngp_lml_workspace_bytes(n, d, nh, arch)
+    ws = _workspace(ws_bytes, x.device)
+    rc = lib.smnngp_lml_f64(_stream(x.device), _p(x), _p(y), n, d, nh, act, arch, _p(hp), KIND[kind], _p(ws),
+                            ws_bytes, _p(out), _p(info))
+    _lib.check(rc, "lml")
+    return out, info
+
+
+def predict(x, y, x_test, *, spec: StackSpec, hp, shift="eps_rel"):
+    """NNGPKernel.predict (spax/kernels.py:29-32): returns (mean [T,C], var [T] = diag(cov), info)."""
+    lib = _lib.load()
+    nh, act, arch = spec.ids()
+    if isinstance(x, np.ndarray):
+        _require_cuda()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        if y.ndim == 1:
+            y = y[:, None]
+        xt = np.ascontiguousarray(x_test, dtype=np.float64)
+        hp = np.ascontiguousarray(hp, dtype=np.float64)
+        n, d = x.shape
+        t, c = xt.shape[0], y.shape[1]
+        mean = np.empty((t, c), dtype=np.float64)
+        var = np.empty(t, dtype=np.float64)
+        info = C.c_int(0)
+        rc = lib.smnngp_predict_host_f64(x.ctypes.data, y.ctypes.data, xt.ctypes.data, n, t, c, d, nh, act, arch,
+                                         hp.ctypes.data, SHIFT[shift], mean.ctypes.data, var.ctypes.data,
+                                         C.byref(info))
+        _lib.check(rc, "predict_host")
+        return mean, var, info.value
+    _require_cuda()
+    x = _f64(x)
+    y = _f64(y, x.device)
+    if y.ndim == 1:
+        y = y[:, None].contiguous()
+    xt = _f64(x_test, x.device)
+    n, d = x.shape
+    t, c = xt.shape[0], y.shape[1]
+    mean = torch.empty((t, c), dtype=torch.float64, device=x.device)
+    var = torch.empty(t, dtype=torch.float64, device=x.device)
+    info = torch.zeros(1, dtype=torch.int32, device=x.device)
+    ws_bytes = lib.smnngp_predict_workspace_bytes(n, t, c, d, nh, arch)
+    ws = _workspace(ws_bytes, x.device)
+    rc = lib.smnngp_predict_f64(_stream(x.device), _p(x), _p(y), _p(xt), n, t, c, d, nh, act, arch, _p(hp),
+                                SHIFT[shift], _p(ws), ws_bytes, _p(mean), _p(var), _p(info))
+    _lib.check(rc, "predict")
+    return mean, var, info
+
+
+def test_nll(x, y, x_test, y_test, y_mean, y_std, *, spec: StackSpec, hp, kind="student_t"):
+    """Fused SPR.test_nll (spax/models.py:100-120).  Returns (nll, mean [T], var [T], info)."""
+    lib = _lib.load()
+    nh, act, arch = spec.ids()
+    if isinstance(x, np.ndarray):
+        _require_cuda()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        xt = np.ascontiguousarray(x_test, dtype=np.float64)
+        yt = np.ascontiguousarray(y_test, dtype=np.float64)
+        hp = np.ascontiguousarray(hp, dtype=np.float64)
+        n, d = x.shape
+        t = xt.shape[0]
+        nll = np.empty(1, dtype=np.float64)
+        mean = np.empty(t, dtype=np.float64)
+        var = np.empty(t, dtype=np.float64)
+        info = C.c_int(0)
+        rc = lib.smnngp_test_nll_host_f64(x.ctypes.data, y.ctypes.data, xt.ctypes.data, yt.ctypes.data, n, t, d, nh,
+                                          act, arch, hp.ctypes.data, KIND[kind], float(y_mean), float(y_std),
+                                          nll.ctypes.data, mean.ctypes.data, var.ctypes.data, C.byref(info))
+        _lib.check(rc, "test_nll_host")
+        return float(nll[0]), mean, var, info.value
+    _require_cuda()
+    x = _f64(x)
+    y = _f64(y, x.device)
+    xt = _f64(x_test, x.device)
+    yt = _f64(y_test, x.device)
+    n, d = x.shape
+    t = xt.shape[0]
+    nll = torch.empty(1, dtype=torch.float64, device=x.device)
+    mean = torch.empty(t, dtype=torch.float64, device=x.device)
+    var = torch.empty(t, dtype=torch.float64, device=x.device)
+    info = torch.zeros(1, dtype=torch.int32, device=x.device)
+    ws_bytes = lib.smnngp_predict_workspace_bytes(n, t, 1, d, nh, arch)
+    ws = _workspace(ws_bytes, x.device)
+    rc = lib.smnngp_test_nll_f64(_stream(x.device), _p(x), _p(y), _p(xt), _p(yt), n, t, d, nh, act, arch, _p(hp),
+                                 KIND[kind], float(y_mean), float(y_std), _p(ws), ws_bytes, _p(nll), _p(mean),
+                                 _p(var), C.c_void_p(0), _p(info))
+    _lib.check(rc, "test_nll")
+    return nll[0], mean, var, info
+
+
+def set_panel_width(nb: int):
+    _lib.load().smnngp_set_panel_width(int(nb))

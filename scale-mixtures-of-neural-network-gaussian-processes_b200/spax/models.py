@@ -1,0 +1,69 @@
+"""SPR with the interface of spax/models.py:81-120.  When the kernel closure is an smnngp ``KernelFn`` and the
+likelihood is one of ours, ``loss`` and ``test_nll`` are single fused C-ABI calls (Gram never leaves the
+device, solves fused into the factorisation); otherwise they compose K / prior_logpdf / predict / logpdf
+exactly like the reference does - every piece still on the CUDA path."""
+import numpy as np
+import torch
+
+from .base import Module, ConstraintTrainVar
+from .bijectors import positive
+from .utils import jitter
+from .. import device as _dev
+from ..nt_kernels import KernelFn
+
+__all__ = ["SPR"]
+
+
+class SPR(Module):
+    def __init__(self, kernel, likelihood, x_data, y_data, y_mean, y_std, *, eps: float = 1e-6):
+        self.kernel = kernel
+        self.likelihood = likelihood
+        self.x_data = x_data
+        self.y_data = y_data
+        self.y_mean = y_mean
+        self.y_std = y_std
+        self.num_data = x_data.shape[0]
+        self.eps = ConstraintTrainVar(eps, constraint=positive())
+
+    def _hp_args(self):
+        lik = self.likelihood
+        a = lik.a.safe_value if hasattr(lik, "a") else 2.0
+        b = lik.b.safe_value if hasattr(lik, "b") else 2.0
+        return dict(eps=self.eps.safe_value, alpha=a, beta=b)
+
+    def _fused(self, kernel_fn):
+        return isinstance(kernel_fn, KernelFn) and getattr(self.likelihood, "kind", None) in _dev.KIND
+
+    def loss(self):
+        kernel_fn = self.kernel.get_kernel_fn()
+        if self._fused(kernel_fn):
+            host = isinstance(self.x_data, np.ndarray)
+            hp = kernel_fn.hp_host(**self._hp_args()) if host else kernel_fn.hp(self.x_data.device, **self._hp_args())
+            out, _ = _dev.lml(self.x_data, self.y_data, spec=kernel_fn.spec, hp=hp, kind=self.likelihood.kind)
+            return float(out[1]) if host else out[1]
+        eps = self.eps.safe_value
+        cov = self.kernel.K(kernel_fn, self.x_data) + jitter(self.num_data, eps=eps, device=self.x_data.device)
+        log_prob = self.likelihood.prior_logpdf(self.y_data, cov)
+        return -log_prob / self.num_data
+
+    def test_nll(self, x, y):
+        kernel_fn = self.kernel.get_kernel_fn()
+        if self._fused(kernel_fn):
+            host = isinstance(self.x_data, np.ndarray)
+            hp = kernel_fn.hp_host(**self._hp_args()) if host else kernel_fn.hp(self.x_data.device, **self._hp_args())
+            nll, _, _, _ = _dev.test_nll(self.x_data, self.y_data, x, y, float(self.y_mean), float(self.y_std),
+                                         spec=kernel_fn.spec, hp=hp, kind=self.likelihood.kind)
+            return nll
+        eps = self.eps.safe_value
+        mean, cov = self.kernel.predict(kernel_fn, self.x_data, self.y_data[:, None], x, eps=eps)
+        require = self.likelihood.require
+        if require:
+            aux_dict = dict(y_data=self.y_data)
+            if "cov_data" in require:
+                aux_dict["cov_data"] = self.kernel.K(kernel_fn, self.x_data)      # models.py:107, no jitter
+            aux = tuple(aux_dict[k] for k in require)
+        else:
+            aux = None
+        log_prob = self.likelihood.logpdf((y * self.y_std) + self.y_mean, (mean.flatten() * self.y_std) + self.y_mean,
+                                          cov * self.y_std ** 2, aux)
+        return -torch.mean(log_prob)

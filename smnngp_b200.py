@@ -1,0 +1,13 @@
+"""Import shim: the package directory is named after the reference repo (hyphens are not importable), so
+``import smnngp_b200`` loads ``scale-mixtures-of-neural-network-gaussian-processes_b200/`` under this name."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                    "scale-mixtures-of-neural-network-gaussian-processes_b200")
+_spec = importlib.util.spec_from_file_location(__name__, os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,254 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances are BASELINE.json's: Gram entries 1e-10 (|dK| <= 1e-10 * max|K|), LML and predictive moments 1e-8
+relative."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from oracle import nngp_oracle as orc
+from tests.synth import regression_data, pixel_data, DEFAULT_HP
+
+pytestmark = pytest.mark.gpu
+
+GRAM_TOL = 1e-10
+LML_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def sm():
+    import torch
+    import smnngp_b200 as s
+    assert torch.cuda.is_available()
+    s._lib.load()
+    return s
+
+
+def _hp(sm, **over):
+    hp = dict(DEFAULT_HP)
+    hp.update(over)
+    return hp, sm.make_hp(hp["w_std"], hp["b_std"], hp["last_w_std"], hp["eps"], hp["alpha"], hp["beta"])
+
+
+def _kw(hp, L, act, arch):
+    return dict(num_hiddens=L, act=act, w_std=hp["w_std"], b_std=hp["b_std"], last_w_std=hp["last_w_std"], arch=arch)
+
+
+@pytest.mark.parametrize("n,d", [(300, 13), (257, 8), (130, 784), (1, 5), (127, 3), (640, 64)])
+@pytest.mark.parametrize("act,arch,L,b_std", [("relu", "mlp", 3, 1e-8), ("erf", "mlp", 3, 0.3),
+                                               ("relu", "resnet", 2, 0.3), ("erf", "resnet", 1, 0.3),
+                                               ("relu", "mlp", 1, 0.0), ("relu", "mlp", 10, 0.1)])
+def test_gram_symmetric(sm, n, d, act, arch, L, b_std):
+    import torch
+    x, *_ = regression_data(n, d, seed=3)
+    hp, hpd = _hp(sm, b_std=b_std, w_std=1.3, last_w_std=0.7)
+    ref = orc.nngp_gram(x, **_kw(hp, L, act, arch))
+    xd = torch.from_numpy(x).cuda()
+    k = sm.device.gram(xd, spec=sm.StackSpec(L, act, arch), hp=hpd).cpu().numpy()
+    err = np.abs(k - ref).max() / np.abs(ref).max()
+    assert err <= GRAM_TOL, f"gram err {err:.3e}"
+    assert np.array_equal(k, k.T), "mirrored output must be exactly symmetric"
+    # lower-only output with the absolute shift on the diagonal
+    kl = sm.device.gram(xd, spec=sm.StackSpec(L, act, arch), hp=hpd, shift="eps_abs", lower_only=True).cpu().numpy()
+    assert np.all(np.triu(kl, 1) == 0.0)
+    ref_l = np.tril(ref + hp["eps"] * np.eye(n))
+    assert np.abs(kl - ref_l).max() / np.abs(ref).max() <= GRAM_TOL
+    # diagonal helper
+    q = sm.device.nngp_diag(xd, spec=sm.StackSpec(L, act, arch), hp=hpd).cpu().numpy()
+    qref = orc.nngp_diag(x, **_kw(hp, L, act, arch))
+    assert np.abs(q - qref).max() <= 1e-12 * np.abs(qref).max()
+
+
+@pytest.mark.parametrize("n,m,d", [(200, 333, 13), (129, 64, 8), (50, 700, 784)])
+@pytest.mark.parametrize("act,arch", [("relu", "mlp"), ("erf", "resnet")])
+def test_gram_cross(sm, n, m, d, act, arch):
+    import torch
+    x, _, x2, *_ = regression_data(n, d, t=m, seed=4)
+    hp, hpd = _hp(sm, b_std=0.2)
+    ref = orc.nngp_gram(x, x2, **_kw(hp, 3, act, arch))
+    k = sm.device.gram(torch.from_numpy(x).cuda(), torch.from_numpy(x2).cuda(), spec=sm.StackSpec(3, act, arch),
+                       hp=hpd).cpu().numpy()
+    assert k.shape == (n, m)
+    assert np.abs(k - ref).max() / np.abs(ref).max() <= GRAM_TOL
+
+
+def test_gram_duplicate_and_zero_rows(sm):
+    """edge cases of the arc-cosine step: identical rows (s -> 0) and all-zero rows (atan2(0, 0) -> pi/2 fill)."""
+    import torch
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((70, 6))
+    x[5] = x[9]
+    x[11] = 0.0
+    x[12] = 0.0
+    hp, hpd = _hp(sm, b_std=0.0)
+    for act in ("relu", "erf"):
+        ref = orc.nngp_gram(x, **_kw(hp, 3, act, "mlp"))
+        k = sm.device.gram(torch.from_numpy(x).cuda(), spec=sm.StackSpec(3, act, "mlp"), hp=hpd).cpu().numpy()
+        assert np.isfinite(k).all()
+        assert np.abs(k - ref).max() <= GRAM_TOL * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n,extra", [(1, 0), (100, 0), (128, 1), (129, 3), (300, 0), (1000, 17), (2500, 1)])
+def test_potrf_vs_lapack(sm, n, extra):
+    import torch
+    rng = np.random.default_rng(n)
+    b = rng.standard_normal((n, n + 8))
+    a = b @ b.T / (n + 8) + 1e-3 * np.eye(n)
+    r = rng.standard_normal((extra, n))
+    buf = np.vstack([a, r])
+    ad = torch.from_numpy(buf).cuda()
+    logdet, info = sm.device.potrf_(ad, n)
+    L = sla.cholesky(a, lower=True)
+    got = ad.cpu().numpy()
+    assert int(info.item()) == 0
+    errL = np.abs(np.tril(got[:n]) - L).max() / np.abs(L).max()
+    assert errL <= 1e-11, f"L err {errL:.3e}"
+    # strict upper triangle untouched
+    assert np.array_equal(np.triu(got[:n], 1), np.triu(a, 1))
+    assert abs(logdet.item() - np.log(np.diag(L)).sum()) <= 1e-10 * max(1.0, abs(np.log(np.diag(L)).sum()))
+    if extra:
+        want = sla.solve_triangular(L, r.T, lower=True).T
+        errR = np.abs(got[n:] - want).max() / np.abs(want).max()
+        assert errR <= 1e-9, f"carried rows err {errR:.3e}"
+
+
+def test_potrf_not_positive_definite(sm):
+    import torch
+    rng = np.random.default_rng(1)
+    n = 300
+    b = rng.standard_normal((n, n))
+    a = b @ b.T / n
+    a[200, 200] = -1.0
+    ad = torch.from_numpy(a.copy()).cuda()
+    logdet, info = sm.device.potrf_(ad)
+    assert int(info.item()) == 201          # LAPACK convention: 1 + first bad pivot
+    assert np.isnan(ad.cpu().numpy()[250, 250])
+
+
+@pytest.mark.parametrize("n,d,L,act,arch,kind", [
+    (506, 13, 3, "relu", "mlp", "student_t"),     # BASELINE config 1
+    (506, 13, 3, "relu", "mlp", "gauss"),
+    (404, 13, 4, "erf", "mlp", "student_t"),
+    (1300, 8, 3, "relu", "resnet", "student_t"),
+    (2100, 8, 3, "relu", "mlp", "student_t"),     # panel width 256 path
+    (77, 5, 2, "relu", "mlp", "gauss"),
+])
+def test_lml_parity(sm, n, d, L, act, arch, kind):
+    import torch
+    x, y, *_ = regression_data(n, d)
+    b_std = 0.3 if act == "erf" else DEFAULT_HP["b_std"]
+    hp, hpd = _hp(sm, b_std=b_std)
+    ref_loss = orc.spr_loss(x, y, kind=kind, a=hp["alpha"], b=hp["beta"], eps=hp["eps"], **_kw(hp, L, act, arch))
+    out, info = sm.device.lml(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), spec=sm.StackSpec(L, act, arch),
+                              hp=hpd, kind=kind)
+    out = out.cpu().numpy()
+    assert int(info.item()) == 0
+    assert abs(out[1] - ref_loss) <= LML_TOL * abs(ref_loss), f"loss {out[1]} vs {ref_loss}"
+    assert abs(out[0] + ref_loss * n) <= LML_TOL * abs(ref_loss * n)
+    # host-buffer C-ABI entry point
+    hph = np.array([hp["w_std"], hp["b_std"], hp["last_w_std"], hp["eps"], hp["alpha"], hp["beta"]])
+    out_h, info_h = sm.device.lml(x, y, spec=sm.StackSpec(L, act, arch), hp=hph, kind=kind)
+    assert info_h == 0 and out_h[1] == out[1], "host and device entry points must agree bitwise"
+
+
+def test_lml_non_pd_gives_nan(sm):
+    """duplicate rows + eps -> 0 makes K singular: reference yields NaN (jax cholesky), never raises."""
+    import torch
+    x, y, *_ = regression_data(200, 4)
+    x[10] = x[20]
+    x[30] = x[20]
+    hp, hpd = _hp(sm, eps=1e-300)
+    out, info = sm.device.lml(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), spec=sm.StackSpec(3, "relu", "mlp"),
+                              hp=hpd)
+    if int(info.item()) != 0:
+        assert np.isnan(out.cpu().numpy()[0])
+
+
+@pytest.mark.parametrize("n,t,d,c,act,arch", [(404, 52, 13, 1, "relu", "mlp"), (900, 130, 8, 3, "erf", "mlp"),
+                                              (1500, 257, 8, 1, "relu", "resnet")])
+def test_predict_parity(sm, n, t, d, c, act, arch):
+    import torch
+    x, y, xt, yt, *_ = regression_data(n, d, t=t)
+    rng = np.random.default_rng(5)
+    Y = y[:, None] if c == 1 else np.column_stack([y] + [rng.standard_normal(n) for _ in range(c - 1)])
+    hp, hpd = _hp(sm, b_std=0.3 if act == "erf" else 1e-8)
+    kw = _kw(hp, 3, act, arch)
+    mean_ref, cov_ref = orc.nt_predict(x, Y, xt, hp["eps"], kernel_kwargs=kw)
+    mean, var, info = sm.device.predict(torch.from_numpy(x).cuda(), torch.from_numpy(Y).cuda(),
+                                        torch.from_numpy(xt).cuda(), spec=sm.StackSpec(3, act, arch), hp=hpd)
+    assert int(info.item()) == 0
+    mean, var = mean.cpu().numpy(), var.cpu().numpy()
+    assert np.abs(mean - mean_ref).max() <= LML_TOL * np.abs(mean_ref).max()
+    vref = np.diag(cov_ref)
+    # variance = k_tt - ||v||^2 cancels: relative 1e-8 on the variance with an absolute floor tied to k_tt
+    ktt = orc.nngp_diag(xt, **kw)
+    assert np.all(np.abs(var - vref) <= LML_TOL * np.abs(vref) + 1e-13 * ktt)
+    # host entry point
+    hph = np.array([hp[k] for k in ("w_std", "b_std", "last_w_std", "eps", "alpha", "beta")])
+    mean_h, var_h, info_h = sm.device.predict(x, Y, xt, spec=sm.StackSpec(3, act, arch), hp=hph)
+    assert info_h == 0 and np.array_equal(mean_h, mean) and np.array_equal(var_h, var)
+
+
+@pytest.mark.parametrize("n,t,d,kind", [(404, 52, 13, "student_t"), (404, 52, 13, "gauss"), (1100, 300, 8, "student_t")])
+def test_test_nll_parity(sm, n, t, d, kind):
+    import torch
+    x, y, xt, yt, ym, ys = regression_data(n, d, t=t)
+    hp, hpd = _hp(sm)
+    kw = _kw(hp, 3, "relu", "mlp")
+    ref, mref, vref = orc.spr_test_nll(x, y, xt, yt, ym, ys, eps=hp["eps"], kind=kind, a=hp["alpha"], b=hp["beta"],
+                                       return_parts=True, **kw)
+    nll, mean, var, info = sm.device.test_nll(*(torch.from_numpy(v).cuda() for v in (x, y, xt, yt)), ym, ys,
+                                              spec=sm.StackSpec(3, "relu", "mlp"), hp=hpd, kind=kind)
+    assert int(info.item()) == 0
+    assert abs(nll.item() - ref) <= LML_TOL * abs(ref), f"{nll.item()} vs {ref}"
+    hph = np.array([hp[k] for k in ("w_std", "b_std", "last_w_std", "eps", "alpha", "beta")])
+    nll_h, *_ = sm.device.test_nll(x, y, xt, yt, ym, ys, spec=sm.StackSpec(3, "relu", "mlp"), hp=hph, kind=kind)
+    assert nll_h == nll.item()
+
+
+def test_spax_api_dropin(sm):
+    """The reference's call pattern (regression/train.py:126-142, spax/models.py) on the mirrored API."""
+    import torch
+    from smnngp_b200.spax import NNGPKernel, StudentTLikelihood, GaussianLikelihood, SPR
+    x, y, xt, yt, ym, ys = regression_data(404, 13, t=52)
+    base = sm.get_mlp_kernel
+
+    def get_kernel_fn(w_std, b_std, last_w_std):
+        return base(3, act="relu", w_std=w_std, b_std=b_std, last_w_std=last_w_std)
+
+    xd, yd, xtd, ytd = (torch.from_numpy(v).cuda() for v in (x, y, xt, yt))
+    for lik, kind in ((StudentTLikelihood(2.0, 2.0), "student_t"), (GaussianLikelihood(), "gauss")):
+        kernel = NNGPKernel(get_kernel_fn, 1.0, 1e-8, 1.0)
+        model = SPR(kernel, lik, xd, yd, ym, ys, eps=1e-6)
+        w, b, v = kernel.get_params()
+        kw = dict(num_hiddens=3, act="relu", w_std=w, b_std=b, last_w_std=v, arch="mlp")
+        ref_loss = orc.spr_loss(x, y, eps=model.eps.safe_value, kind=kind, a=2.0, b=2.0, **kw)
+        ref_nll = orc.spr_test_nll(x, y, xt, yt, ym, ys, eps=model.eps.safe_value, kind=kind, a=2.0, b=2.0, **kw)
+        loss = float(model.loss())
+        nll = float(model.test_nll(xtd, ytd))
+        assert abs(loss - ref_loss) <= LML_TOL * abs(ref_loss)
+        assert abs(nll - ref_nll) <= LML_TOL * abs(ref_nll)
+        # un-fused composition (K + jitter -> prior_logpdf; predict -> logpdf), as the reference writes it
+        kernel_fn = kernel.get_kernel_fn()
+        cov = kernel.K(kernel_fn, xd) + sm.spax.jitter(404, eps=model.eps.safe_value)
+        lp = float(lik.prior_logpdf(yd, cov))
+        assert abs(-lp / 404 - ref_loss) <= LML_TOL * abs(ref_loss)
+        mean, var = kernel.predict(kernel_fn, xd, yd[:, None], xtd, eps=model.eps.safe_value)
+        aux = (kernel.K(kernel_fn, xd), yd) if lik.require else None
+        logp = lik.logpdf(ytd * ys + ym, mean.flatten() * ys + ym, var * ys ** 2, aux)
+        assert abs(-float(logp.mean()) - ref_nll) <= LML_TOL * abs(ref_nll)
+    # numpy inputs go through the host-buffer C-ABI
+    model_h = SPR(NNGPKernel(get_kernel_fn, 1.0, 1e-8, 1.0), StudentTLikelihood(2.0, 2.0), x, y, ym, ys)
+    assert isinstance(model_h.loss(), float)
+
+
+def test_medium_lml_pixel_shape(sm):
+    """MNIST-shaped inputs at a size the oracle still finishes in seconds (D = 784, two outer panels)."""
+    import torch
+    x, y, *_ = pixel_data(3000, 784)
+    hp, hpd = _hp(sm)
+    ref = orc.spr_loss(x, y, eps=hp["eps"], kind="student_t", a=2.0, b=2.0, **_kw(hp, 3, "relu", "mlp"))
+    out, info = sm.device.lml(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), spec=sm.StackSpec(3, "relu", "mlp"),
+                              hp=hpd)
+    assert int(info.item()) == 0
+    assert abs(out[1].item() - ref) <= LML_TOL * abs(ref)
