@@ -71,28 +71,89 @@ cudaError_t launch_gemm_t(cudaStream_t s, const GemmParams& p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Diagonal block: Cholesky + inverse of the factor in one in-place elimination.
-// State G (lower, shared memory).  At step j the pivot vector v holds  v[c<j] = W[j][c] (partial inverse
-// row), v[j] = d (pivot), v[c>j] = S[c][j] (current column).  Every row i > j then does
-//   G[i][c] -= v[i] * v[c] / d      (c <= i, c != j),      G[i][j] = -v[i] / d
-// which is simultaneously the Schur update of the trailing matrix (c > j) and the forward substitution for
-// inv(L) (c < j).  L^T is parked in the unused upper triangle, inv(L) ends up in the lower triangle.
-// One __syncthreads per column.
+// Diagonal block (w <= 128): Cholesky factor AND its inverse in one CTA, blocked by 32 columns.
+//   per 32-block b:  warp 0 factors the 32x32 diagonal block in registers (lane = row, pivots and column
+//                    entries exchanged with warp shuffles) and inverts the factor (lane = column, forward
+//                    substitution with broadcast shared-memory reads);
+//                    all warps: panel below = S_ib * inv(L_bb)^T and trailing update S -= P P^T, both as
+//                    8x8x4 DMMA tiles straight out of shared memory (row strips of 8, conflict-free ld 132);
+//   afterwards inv(L) is assembled block-wise:  X_ii = inv(L_ii),  X_ik = -X_ii * sum_{m=k}^{i-1} L_im X_mk,
+//   the off-diagonal X blocks living in the otherwise unused upper triangle of the shared-memory matrix.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int PF_THREADS = 512;
-constexpr int GLD = PB + 1;
-constexpr int PF_SMEM_BYTES = (PB * GLD + 3 * PB + 32) * 8;
+constexpr int PF_THREADS = 256;
+constexpr int PF_WARPS = PF_THREADS / 32;
+constexpr int DB = 32;                 // register-resident diagonal block
+constexpr int GLD = PB + 4;            // 132: (4 * row + k) mod 16 distinct over a half-warp's 4 rows x 4 k
+constexpr int MLD = DB + 4;            // 36: same property
+constexpr int PF_SMEM_BYTES = (PB * GLD + 4 * DB * MLD + 64) * 8;
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// warp 0, lane = row: factor the 32x32 block at Gbb (lower part valid), write L back (lower) and inv(L) to M.
+__device__ __forceinline__ void diag32_factor_invert(double* __restrict__ Gbb, double* __restrict__ M, int lane,
+                                                     int col_base, int& bad) {
+  double a[DB];
+#pragma unroll
+  for (int c = 0; c < DB; c++) a[c] = Gbb[lane * GLD + c];
+#pragma unroll
+  for (int j = 0; j < DB; j++) {
+    double d = shfl_d(a[j], j);
+    if (!(d > 0.0)) {                 // non-PD (or NaN input): mirror lax.linalg.cholesky -> NaN, no abort
+      if (bad == 0) bad = col_base + j + 1;
+      d = __longlong_as_double(0x7ff8000000000000ll);
+    }
+    const double rinv = rsqrt(d);
+    const double l = (lane == j) ? d * rinv : a[j] * rinv;   // lane j: L_jj = sqrt(d); lanes > j: L_ij
+    a[j] = l;
+#pragma unroll
+    for (int c = j + 1; c < DB; c++) a[c] = fma(-l, shfl_d(l, c), a[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < DB; c++)
+    if (c <= lane) Gbb[lane * GLD + c] = a[c];
+  __syncwarp();
+  // inverse, lane = column c: x_i = (delta_ic - sum_{k=c}^{i-1} L_ik x_k) / L_ii   (L_ik: broadcast reads)
+  double x[DB];
+#pragma unroll
+  for (int i = 0; i < DB; i++) {
+    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < i; k += 2) {
+      s0 = fma(-Gbb[i * GLD + k], x[k], s0);
+      if (k + 1 < i) s1 = fma(-Gbb[i * GLD + k + 1], x[k + 1], s1);
+    }
+    const double v = (s0 + s1) / Gbb[i * GLD + i];
+    x[i] = (i >= lane) ? v : 0.0;     // rows above the column's diagonal stay exactly zero
+  }
+#pragma unroll
+  for (int i = 0; i < DB; i++) M[i * MLD + lane] = x[i];
+}
+
+// acc(8x8) += sum over nks k4-steps of A[row, k] * B[col, k]; A, B K-contiguous (element (r, k) at p[r*ld + k])
+__device__ __forceinline__ void tile_nt(double (&acc)[2], const double* __restrict__ A, int lda,
+                                        const double* __restrict__ B, int ldb, int nks, int lane) {
+  const double* ap = A + (lane >> 2) * lda + (lane & 3);
+  const double* bp = B + (lane >> 2) * ldb + (lane & 3);
+  for (int ks = 0; ks < nks; ks++) dmma8x8x4(acc, ap[ks * 4], bp[ks * 4]);
+}
+// same with B k-major: element (k, col) at B[k*ldb + col]
+__device__ __forceinline__ void tile_nn(double (&acc)[2], const double* __restrict__ A, int lda,
+                                        const double* __restrict__ B, int ldb, int nks, int lane) {
+  const double* ap = A + (lane >> 2) * lda + (lane & 3);
+  const double* bp = B + (lane & 3) * ldb + (lane >> 2);
+  for (int ks = 0; ks < nks; ks++) dmma8x8x4(acc, ap[ks * 4], bp[ks * 4 * ldb]);
+}
 
 __global__ void __launch_bounds__(PF_THREADS, 1)
 potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restrict__ Linv,
                    double* __restrict__ logdet, int* __restrict__ info, int gcol0) {
   extern __shared__ __align__(16) double sm[];
-  double* G = sm;
-  double* v0 = G + PB * GLD;
-  double* v1 = v0 + PB;
-  double* dl = v1 + PB;
-  double* red = dl + PB;
+  double* G = sm;                          // [128][132]
+  double* Mi = G + PB * GLD;               // 4 x [32][36] inverse diagonal blocks
+  double* red = Mi + 4 * DB * MLD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nblk = (w + DB - 1) / DB;
+  const int wp = nblk * DB;                // padded size (identity padding)
 
   for (int idx = tid; idx < PB * PB; idx += PF_THREADS) {
     int i = idx >> 7, c = idx & (PB - 1);
@@ -101,51 +162,118 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
     else if (i == c) g = 1.0;
     G[i * GLD + c] = g;
   }
-  if (tid < PB) { dl[tid] = 1.0; v1[tid] = 0.0; }
-  __syncthreads();
-  if (tid < PB) v0[tid] = G[tid * GLD];
   __syncthreads();
 
   int bad = 0;
-  for (int j = 0; j < w; j++) {
-    const double* vb = (j & 1) ? v1 : v0;
-    double* vn = (j & 1) ? v0 : v1;
-    double d = vb[j];
-    if (!(d > 0.0)) {               // non-PD (or NaN input): mirror lax.linalg.cholesky -> NaN, no abort
-      if (bad == 0) bad = j + 1;
-      d = __longlong_as_double(0x7ff8000000000000ll);
+  for (int b = 0; b < nblk; b++) {
+    const int b0 = b * DB;
+    if (warp == 0) diag32_factor_invert(G + b0 * GLD + b0, Mi + b * DB * MLD, lane, b0, bad);
+    __syncthreads();
+    const int r_first = b0 + DB;
+    const int nstrips = (wp - r_first) / 8;
+    // panel: rows below, P = S_ib * inv(L_bb)^T   (a warp owns whole 8-row strips -> in place)
+    for (int s = warp; s < nstrips; s += PF_WARPS) {
+      const int r0 = r_first + s * 8;
+      double af[8];
+      const double* ap = G + (r0 + (lane >> 2)) * GLD + b0 + (lane & 3);
+#pragma unroll
+      for (int ks = 0; ks < 8; ks++) af[ks] = ap[ks * 4];
+      double acc[4][2];
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        acc[nt][0] = acc[nt][1] = 0.0;
+        const double* bp = Mi + b * DB * MLD + (nt * 8 + (lane >> 2)) * MLD + (lane & 3);
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++)
+          if (ks <= 2 * nt + 1) dmma8x8x4(acc[nt], af[ks], bp[ks * 4]);   // inv(L) is lower triangular
+      }
+      __syncwarp();
+      double* op = G + (r0 + (lane >> 2)) * GLD + b0 + (lane & 3) * 2;
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) { op[nt * 8] = acc[nt][0]; op[nt * 8 + 1] = acc[nt][1]; }
     }
-    const double dinv = 1.0 / d;
-    if (tid < PB) {
-      const double r = sqrt(d);
-      const double rinv = 1.0 / r;
-      if (tid == j) {
-        dl[j] = r;
-        G[j * GLD + j] = rinv;
-      } else {
-        G[j * GLD + tid] = vb[tid] * rinv;   // tid > j: L[tid][j] (stored transposed); tid < j: inv(L)[j][tid]
+    __syncthreads();
+    // trailing update: S_ic -= P_i P_c^T for r_first <= c-tile <= row strip
+    for (int s = warp; s < nstrips; s += PF_WARPS) {
+      const int r0 = r_first + s * 8;
+      double af[8];
+      const double* ap = G + (r0 + (lane >> 2)) * GLD + b0 + (lane & 3);
+#pragma unroll
+      for (int ks = 0; ks < 8; ks++) af[ks] = ap[ks * 4];
+      for (int c0 = r_first; c0 <= r0; c0 += 8) {
+        double acc[2] = {0.0, 0.0};
+        const double* bp = G + (c0 + (lane >> 2)) * GLD + b0 + (lane & 3);
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) dmma8x8x4(acc, af[ks], bp[ks * 4]);
+        double* cp = G + (r0 + (lane >> 2)) * GLD + c0 + (lane & 3) * 2;
+        cp[0] -= acc[0];
+        cp[1] -= acc[1];
       }
     }
-    for (int i = j + 1 + warp; i < w; i += PF_THREADS / 32) {
-      const double f = vb[i] * dinv;
-      double* gi = G + i * GLD;
-      for (int c = lane; c <= i; c += 32) {
-        double g = (c == j) ? -f : gi[c] - f * vb[c];
-        gi[c] = g;
-        if (i == j + 1) vn[c] = g;
-        else if (c == j + 1) vn[i] = g;
+    __syncthreads();
+  }
+
+  // ---- inverse assembly: X_ik (i > k) is kept at block position (k, i) of G (upper triangle, untransposed)
+  for (int dist = 1; dist < nblk; dist++) {
+    const int npairs = nblk - dist;
+    // phase A: T_ik = sum_{m=k}^{i-1} L_im X_mk ; 16 output tiles per pair
+    for (int u = warp; u < npairs * 16; u += PF_WARPS) {
+      const int k = u >> 4, t = u & 15, i = k + dist;
+      const int tr = (t >> 2) * 8, tc = (t & 3) * 8;
+      double acc[2] = {0.0, 0.0};
+      for (int m = k; m < i; m++) {
+        const double* Lim = G + (i * DB + tr) * GLD + m * DB;
+        if (m == k) tile_nn(acc, Lim, GLD, Mi + k * DB * MLD + tc, MLD, 8, lane);
+        else tile_nn(acc, Lim, GLD, G + (k * DB) * GLD + m * DB + tc, GLD, 8, lane);
+      }
+      // T is written to its final place (k, i); nobody reads that block in this phase
+      double* tp = G + (k * DB + tr + (lane >> 2)) * GLD + i * DB + tc + (lane & 3) * 2;
+      tp[0] = acc[0];
+      tp[1] = acc[1];
+    }
+    __syncthreads();
+    // phase B: X_ik = -inv(L_ii) T_ik in place; a warp owns an 8-column strip of one block
+    for (int u = warp; u < npairs * 4; u += PF_WARPS) {
+      const int k = u >> 2, tc = (u & 3) * 8, i = k + dist;
+      double* T = G + (k * DB) * GLD + i * DB + tc;
+      double bf[8];
+#pragma unroll
+      for (int ks = 0; ks < 8; ks++) bf[ks] = T[(ks * 4 + (lane & 3)) * GLD + (lane >> 2)];
+      double acc[4][2];
+#pragma unroll
+      for (int rt = 0; rt < 4; rt++) {
+        acc[rt][0] = acc[rt][1] = 0.0;
+        const double* ap = Mi + i * DB * MLD + (rt * 8 + (lane >> 2)) * MLD + (lane & 3);
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++)
+          if (ks <= 2 * rt + 1) dmma8x8x4(acc[rt], ap[ks * 4], bf[ks]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int rt = 0; rt < 4; rt++) {
+        double* op = T + (rt * 8 + (lane >> 2)) * GLD + (lane & 3) * 2;
+        op[0] = -acc[rt][0];
+        op[1] = -acc[rt][1];
       }
     }
     __syncthreads();
   }
 
   for (int idx = tid; idx < PB * PB; idx += PF_THREADS) {
-    int i = idx >> 7, c = idx & (PB - 1);
-    if (i < w && c <= i) A[(long long)i * lda + c] = (c == i) ? dl[i] : G[c * GLD + i];
-    Linv[idx] = (c <= i) ? G[i * GLD + c] : 0.0;
+    const int i = idx >> 7, c = idx & (PB - 1);
+    if (i < w && c <= i) A[(long long)i * lda + c] = G[i * GLD + c];
+    double v = 0.0;
+    if (i < wp && c <= i) {
+      const int bi = i / DB, bc = c / DB;
+      v = (bi == bc) ? Mi[bi * DB * MLD + (i - bi * DB) * MLD + (c - bc * DB)]
+                     : G[(bc * DB + (i - bi * DB)) * GLD + bi * DB + (c - bc * DB)];
+    } else if (i == c) {
+      v = 1.0;
+    }
+    Linv[idx] = v;
   }
   // sum of log L_ii in a fixed order
-  double lg = (tid < w) ? log(dl[tid]) : 0.0;
+  double lg = (tid < w) ? log(G[tid * GLD + tid]) : 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
   if (lane == 0) red[warp] = lg;

@@ -34,9 +34,9 @@ constexpr int SC_QUAD = 6;       // ||L^-1 y||^2
 constexpr int SC_COUNT = 16;
 
 __device__ __forceinline__ void dmma8x8x4(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c[0]), "+d"(c[1])
-               : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c[0]), "+d"(c[1])
+      : "d"(a), "d"(b));
 }
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src, int src_bytes) {

@@ -7,34 +7,36 @@
 
 namespace smnngp {
 
-// Stage one 128 x BK operand tile.  g points at (first tile row, k = 0); rows >= rows_valid and k >= K zero-fill.
+// Per-thread addressing of the cp.async staging, hoisted out of the k loop.  Each thread copies the same
+// (row, k-chunk) slots of every slab: 4 x 16 B (aligned operands) or 8 x 8 B.
 template <bool ALIGN16>
-__device__ __forceinline__ void load_operand_tile(double* s, const double* __restrict__ g, long long ld,
-                                                  int rows_valid, int k0, int K, int tid) {
-  if (ALIGN16) {
+struct TileLoader {
+  static constexpr int NCH = ALIGN16 ? 4 : 8;
+  const double* src[NCH];   // global address of the slot at k0 = 0 (nullptr: row out of range -> always zero fill)
+  int soff[NCH];            // smem offset (doubles) inside the operand tile
+  int kc[NCH];              // k offset of the slot inside a slab
+  __device__ __forceinline__ void init(const double* __restrict__ g, long long ld, int rows_valid, int tid) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < NCH; i++) {
       int c = tid + i * GEMM_THREADS;
-      int r = c >> 3;
-      int kc = (c & 7) * 2;
-      int rem = K - (k0 + kc);
-      int bytes = 0;
-      if (r < rows_valid && rem > 0) bytes = rem >= 2 ? 16 : 8;
-      const double* src = bytes ? g + (long long)r * ld + (k0 + kc) : g;
-      cp_async16(s + r * LDK + kc, src, bytes);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      int c = tid + i * GEMM_THREADS;
-      int r = c >> 4;
-      int kc = c & 15;
-      int bytes = (r < rows_valid && (k0 + kc) < K) ? 8 : 0;
-      const double* src = bytes ? g + (long long)r * ld + (k0 + kc) : g;
-      cp_async8(s + r * LDK + kc, src, bytes);
+      int r = ALIGN16 ? (c >> 3) : (c >> 4);
+      kc[i] = ALIGN16 ? (c & 7) * 2 : (c & 15);
+      soff[i] = r * LDK + kc[i];
+      src[i] = (r < rows_valid) ? g + (long long)r * ld + kc[i] : nullptr;
     }
   }
-}
+  __device__ __forceinline__ void issue(double* s, int k0, int K, const double* dummy) const {
+#pragma unroll
+    for (int i = 0; i < NCH; i++) {
+      int rem = K - (k0 + kc[i]);
+      int bytes = 0;
+      if (src[i] != nullptr && rem > 0) bytes = ALIGN16 ? (rem >= 2 ? 16 : 8) : 8;
+      const double* p = bytes ? src[i] + k0 : dummy;
+      if (ALIGN16) cp_async16(s + soff[i], p, bytes);
+      else cp_async8(s + soff[i], p, bytes);
+    }
+  }
+};
 
 // Accumulator element acc[mi][ni][e] is C(row, col) with
 //   row = wm*64 + mi*8 + (lane>>2),  col = wn*32 + ni*8 + (lane&3)*2 + e      (wm = warp>>2, wn = warp&3)
@@ -50,12 +52,15 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[MI][NI][2], const do
 #pragma unroll
     for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
+  TileLoader<ALIGN16> la, lb;
+  la.init(Ag, lda, a_rows, tid);
+  lb.init(Bg, ldb, b_rows, tid);
 #pragma unroll
   for (int s = 0; s < STAGES - 1; s++) {
     if (s < KT) {
       double* st = smem + s * STAGE_DOUBLES;
-      load_operand_tile<ALIGN16>(st, Ag, lda, a_rows, s * BK, K, tid);
-      load_operand_tile<ALIGN16>(st + BM * LDK, Bg, ldb, b_rows, s * BK, K, tid);
+      la.issue(st, s * BK, K, Ag);
+      lb.issue(st + BM * LDK, s * BK, K, Bg);
     }
     cp_async_commit();
   }
@@ -63,15 +68,6 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[MI][NI][2], const do
   for (int kt = 0; kt < KT; kt++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {
-      int nk = kt + STAGES - 1;
-      if (nk < KT) {
-        double* st = smem + (nk % STAGES) * STAGE_DOUBLES;
-        load_operand_tile<ALIGN16>(st, Ag, lda, a_rows, nk * BK, K, tid);
-        load_operand_tile<ALIGN16>(st + BM * LDK, Bg, ldb, b_rows, nk * BK, K, tid);
-      }
-      cp_async_commit();
-    }
     const double* As = smem + (kt % STAGES) * STAGE_DOUBLES;
     const double* ap = As + (wm * 64) * LDK + frag_off;
     const double* bp = As + BM * LDK + (wn * 32) * LDK + frag_off;
@@ -86,6 +82,17 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[MI][NI][2], const do
       for (int mi = 0; mi < MI; mi++)
 #pragma unroll
         for (int ni = 0; ni < NI; ni++) dmma8x8x4(acc[mi][ni], a[mi], b[ni]);
+      if (kk == 0) {
+        // refill the stage consumed in the previous iteration; issued after the first DMMA group so the
+        // tensor pipe is already busy while the copy instructions go out
+        int nk = kt + STAGES - 1;
+        if (nk < KT) {
+          double* st = smem + (nk % STAGES) * STAGE_DOUBLES;
+          la.issue(st, nk * BK, K, Ag);
+          lb.issue(st + BM * LDK, nk * BK, K, Bg);
+        }
+        cp_async_commit();
+      }
     }
   }
   cp_async_wait<0>();
