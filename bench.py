@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py - the hot path of BASELINE.json on synthetic data: 3-layer ReLU NNGP Gram + Cholesky + Student-t
+log marginal likelihood in FP64 at N = 60 000, D = 784 (MNIST-shaped), one "step" = one full evaluation of
+SPR.loss (spax/models.py:93-98) on one batch of inputs.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N = 1 runs the single-GPU fused C-ABI call; N > 1 (under torchrun, one rank per GPU) runs the block-cyclic
+distributed driver over NCCL on the SAME fixed problem (strong scaling).  Prints ONE JSON line on rank 0.
+`--impl reference` times the CPU restatement of the reference path (oracle/, NumPy + LAPACK + OpenMP C
+recursion - the reference's own JAX/neural_tangents stack is not installable here) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "NNGP Gram+Cholesky+Student-t LML time & FP64 TFLOP/s, N=60k, 1/2/4/8 B200"
+UNIT = "TFLOP/s"
+HP = dict(w_std=1.0, b_std=1e-8, last_w_std=1.0, eps=1e-6, alpha=2.0, beta=2.0)   # regression/train.py:37-45
+NUM_HIDDENS = 3
+CPU_SAMPLE_N = 12000
+
+
+def lml_flops(n, d):
+    """Algorithmic flops: symmetric Gram N(N+1)D + Cholesky N^3/3 + triangular solve N^2."""
+    return n * (n + 1.0) * d + n ** 3 / 3.0 + float(n) * n
+
+
+def make_inputs(n, d, seed=10):
+    from tests.synth import pixel_data
+    x, y, *_ = pixel_data(n, d, seed=seed)
+    return x, y
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([v.strip() for v in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_step(x, y):
+    """One LML evaluation by the CPU port of the reference path (all host threads BLAS/LAPACK/OpenMP)."""
+    from oracle import nngp_oracle as orc
+    t0 = time.perf_counter()
+    loss = orc.spr_loss(x, y, num_hiddens=NUM_HIDDENS, act="relu", arch="mlp", w_std=HP["w_std"],
+                        b_std=HP["b_std"], last_w_std=HP["last_w_std"], eps=HP["eps"], kind="student_t",
+                        a=HP["alpha"], b=HP["beta"], fast=True)
+    return time.perf_counter() - t0, loss
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        n = 1
+    return max(n, 1), os.cpu_count()
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, d = min(args.n, CPU_SAMPLE_N), args.d
+    x, y = make_inputs(n, d)
+    for _ in range(args.warmup):
+        cpu_port_step(x, y)
+    times = [cpu_port_step(x, y)[0] for _ in range(args.steps)]
+    t = float(np.mean(times))
+    val = lml_flops(n, d) / t * 1e-12
+    blas_threads, cores = host_threads()
+    sample = (f"first {n} of the {args.n} rows of the same synthetic workload (D={d}, L=3 ReLU, Student-t LML); "
+              f"the full N would need ~{(args.n / n) ** 3 * t / 60:.0f} min of CPU time")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3 NNGP Gram+Cholesky+Student-t LML, N={args.n} D={d} L=3 relu (CPU sample N={n})"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": blas_threads, "host_cpus": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import smnngp_b200 as sm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device and no CPU fallback exists for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = sm._lib.load()
+    n, d = args.n, args.d
+    flops = lml_flops(n, d)
+    spec = sm.StackSpec(NUM_HIDDENS, "relu", "mlp")
+    hp_dev = sm.make_hp(device=dev, **HP)
+    x_np, y_np = make_inputs(n, d)
+
+    if world > 1:
+        from smnngp_b200 import distributed as smd
+        solver = smd.DistributedLML(n, d, spec, dev)
+        xd = torch.from_numpy(x_np).to(dev)
+        yd = torch.from_numpy(y_np).to(dev)
+
+        def step():
+            return solver.lml(xd, yd, hp_dev, kind="student_t")
+    else:
+        xd = torch.from_numpy(x_np).to(dev)
+        yd = torch.from_numpy(y_np).to(dev)
+
+        def step():
+            return sm.device.lml(xd, yd, spec=spec, hp=hp_dev, kind="student_t")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    lib.smnngp_instr_reset(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out = step()
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = int(lib.smnngp_instr_launches())
+    import ctypes as C
+    upd_ms, upd_flops = C.c_double(0), C.c_double(0)
+    n_upd = lib.smnngp_instr_updates(C.byref(upd_ms), C.byref(upd_flops))
+    lib.smnngp_instr_reset(0)
+    if world > 1:
+        tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_total = float(tmax.item())
+        lsum = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+        dist.all_reduce(lsum)
+        launches = int(lsum.item())
+    ms_step = ms_total / args.steps
+    value = flops / (ms_step * 1e-3) * 1e-12
+    res = out[0] if isinstance(out, tuple) else out
+    loss = float(res[1].item()) if hasattr(res, "__len__") else float(res)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
+    e2e = None
+    if world == 1:
+        from smnngp_b200.spax import NNGPKernel, StudentTLikelihood, SPR
+        xp = torch.from_numpy(x_np).pin_memory()
+        yp = torch.from_numpy(y_np).pin_memory()
+
+        def get_kernel_fn(w_std, b_std, last_w_std):
+            return sm.get_mlp_kernel(NUM_HIDDENS, act="relu", w_std=w_std, b_std=b_std, last_w_std=last_w_std)
+
+        model = SPR(NNGPKernel(get_kernel_fn, HP["w_std"], HP["b_std"], HP["last_w_std"]),
+                    StudentTLikelihood(HP["alpha"], HP["beta"]), xp.numpy(), yp.numpy(), 0.0, 1.0, eps=HP["eps"])
+        sm.device.release_workspaces()
+        torch.cuda.empty_cache()
+        model.loss()                                    # warm-up (arena allocation)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        k_e2e = max(1, min(args.steps, 3))
+        for _ in range(k_e2e):
+            loss_e2e = model.loss()
+        t_e2e = (time.perf_counter() - t0) / k_e2e
+        e2e = {"value": flops / t_e2e * 1e-12, "unit": UNIT, "ms_per_step": t_e2e * 1e3,
+               "h2d_bytes_per_step": int(x_np.nbytes + y_np.nbytes + 6 * 8), "d2h_bytes_per_step": 4 * 8 + 4,
+               "api": "spax.SPR.loss() on pinned NumPy inputs -> smnngp_lml_host_f64", "loss": loss_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (Cholesky trailing update, FP64 tensor pipe) ----
+    peak = float(lib.smnngp_dmma_peak_tflops())
+    achieved = (upd_flops.value / (upd_ms.value * 1e-3) * 1e-12) if upd_ms.value > 0 else None
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel<EPI_SUB> (Cholesky trailing update C -= P P^T, DMMA.8x8x4)",
+                "achieved": achieved, "peak": peak, "unit": UNIT,
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "launches_timed": int(n_upd), "kernel_ms_per_step": upd_ms.value / args.steps,
+                "peak_source": "register-resident DMMA.8x8x4 issue-rate probe run live on this GPU "
+                               "(smnngp_dmma_peak_tflops; MEASURED_PEAKS.json has no FP64 figure; "
+                               "profiles/r01_fp64_peak.txt: 37.1 TF/s, cuBLAS Dgemm 36.0)"}
+
+    # ---- CPU baseline: the oracle port on a bounded sample, rank 0, N = 1 only ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ns = min(n, CPU_SAMPLE_N)
+        xs, ys = x_np[:ns], y_np[:ns]
+        t_cpu, _ = cpu_port_step(xs, ys)
+        blas_threads, cores = host_threads()
+        cpu = {"value": lml_flops(ns, d) / t_cpu * 1e-12, "unit": UNIT, "cores": blas_threads, "host_cpus": cores,
+               "kind": "port", "seconds": t_cpu,
+               "sample": f"first {ns} of the {n} rows of the same inputs (full N extrapolates to "
+                         f"~{(n / ns) ** 3 * t_cpu / 60:.0f} min)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3 NNGP Gram+Cholesky+Student-t LML, N={n} D={d} L=3 relu, eps=1e-6 a=b=2",
+                       "algorithmic_flops_per_step": flops,
+                       "l2": "working set 8*N^2 B >> 126 MB L2 (inputs larger than L2, no explicit flush)",
+                       "parallelism": "1 GPU fused call" if world == 1 else f"block-row cyclic over {world} GPUs, NCCL"},
+            "loss": loss, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--n", type=int, default=60000)
+    ap.add_argument("--d", type=int, default=784)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

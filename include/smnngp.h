@@ -119,6 +119,14 @@ void smnngp_host_release(void);
 /* tuning knob: outer panel width of the Cholesky (multiple of 128; 0 = automatic) */
 void smnngp_set_panel_width(int nb);
 
+/* ---- instrumentation (bench.py; no reference counterpart): kernel-launch counter, CUDA-event timing of the
+ * Cholesky trailing updates (the dominant kernel) and a register-resident DMMA.8x8x4 issue-rate probe that
+ * measures the FP64 tensor peak of the device the roofline fraction is quoted against. */
+void smnngp_instr_reset(int time_updates);
+long long smnngp_instr_launches(void);
+int smnngp_instr_updates(double* total_ms, double* alg_flops);
+double smnngp_dmma_peak_tflops(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,17 +99,51 @@ def _recursion(k, q1, q2, *, num_hiddens, act, w_std, b_std, last_w_std, arch):
     return k, v2 * q1, v2 * q2
 
 
+_CLIB = None
+
+
+def _c_recursion():
+    """Optional multi-threaded C restatement (oracle/nngp_recursion.c, built by oracle/Makefile)."""
+    global _CLIB
+    if _CLIB is None:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libnngp_recursion.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle`")
+        lib = ctypes.CDLL(path)
+        lib.nngp_recursion_inplace.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_double, ctypes.c_double, ctypes.c_double]
+        _CLIB = lib
+    return _CLIB
+
+
 def nngp_gram(x1, x2=None, *, num_hiddens, act="relu", w_std=1.0, b_std=0.0, last_w_std=1.0, arch="mlp",
-              row_block=4096):
+              row_block=4096, fast=False):
     """``kernel_fn(x1, x2, get="nngp")`` (spax/kernels.py:23-27) for the MLP / dense-resnet stacks.
 
     x1 [N,D], x2 [M,D] or None (=> x1).  Returns K [N,M] float64.  Evaluated in row blocks to bound memory.
+    fast=True runs the layer recursion in the OpenMP C restatement (same arithmetic, all host cores) - used for
+    the timed CPU baseline.
     """
     x1 = np.ascontiguousarray(x1, dtype=np.float64)
     x2 = x1 if x2 is None else np.ascontiguousarray(x2, dtype=np.float64)
     d = x1.shape[1]
     q1 = np.einsum("ij,ij->i", x1, x1) / d
     q2 = q1 if x2 is x1 else np.einsum("ij,ij->i", x2, x2) / d
+    if fast:
+        if act not in ACTS:
+            raise KeyError("Unsupported act '{}'".format(act))
+        if arch not in ARCHS:
+            raise ValueError(f"Unsupported network '{arch}'")
+        k = (x1 @ x2.T) / d
+        rc = _c_recursion().nngp_recursion_inplace(k.ctypes.data, k.shape[0], k.shape[1], q1.ctypes.data,
+                                                   q2.ctypes.data, int(num_hiddens), ACTS.index(act),
+                                                   ARCHS.index(arch), float(w_std), float(b_std), float(last_w_std))
+        if rc != 0:
+            raise MemoryError("nngp_recursion_inplace")
+        return k
     out = np.empty((x1.shape[0], x2.shape[0]), dtype=np.float64)
     kw = dict(num_hiddens=num_hiddens, act=act, w_std=w_std, b_std=b_std, last_w_std=last_w_std, arch=arch)
     for r0 in range(0, x1.shape[0], row_block):
@@ -173,11 +207,11 @@ def prior_logpdf(y, cov, *, kind, a=None, b=None):
 
 
 def spr_loss(x, y, *, num_hiddens, act="relu", w_std=1.0, b_std=0.0, last_w_std=1.0, arch="mlp", eps=1e-6,
-             kind="student_t", a=2.0, b=2.0):
+             kind="student_t", a=2.0, b=2.0, fast=False):
     """SPR.loss (spax/models.py:93-98): -prior_logpdf(y, K + eps I) / N."""
     n = x.shape[0]
     cov = nngp_gram(x, num_hiddens=num_hiddens, act=act, w_std=w_std, b_std=b_std, last_w_std=last_w_std,
-                    arch=arch)
+                    arch=arch, fast=fast)
     cov[np.diag_indices(n)] += eps                                  # == + jitter(n, eps) without the N x N eye
     return -prior_logpdf(y, cov, kind=kind, a=a, b=b) / n
 

@@ -25,6 +25,7 @@ EXPORTS = [
     "smnngp_lml_workspace_bytes", "smnngp_lml_f64", "smnngp_predict_workspace_bytes", "smnngp_predict_f64",
     "smnngp_test_nll_f64", "smnngp_lml_host_f64", "smnngp_predict_host_f64", "smnngp_test_nll_host_f64",
     "smnngp_host_release", "smnngp_set_panel_width",
+    "smnngp_instr_reset", "smnngp_instr_launches", "smnngp_instr_updates", "smnngp_dmma_peak_tflops",
 ]
 
 
@@ -108,6 +109,11 @@ def _declare(lib):
     lib.smnngp_host_release.restype = None
     lib.smnngp_set_panel_width.restype = None
     lib.smnngp_set_panel_width.argtypes = [_i]
+    lib.smnngp_instr_reset.restype = None
+    lib.smnngp_instr_reset.argtypes = [_i]
+    lib.smnngp_instr_launches.restype = C.c_longlong
+    lib.smnngp_instr_updates.argtypes = [_vp, _vp]
+    lib.smnngp_dmma_peak_tflops.restype = _d
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("smnngp_abi_version",):

@@ -147,6 +147,26 @@ int smnngp_abi_version(void) { return SMNNGP_ABI_VERSION; }
 const char* smnngp_last_error(void) { return g_err.c_str(); }
 void smnngp_set_panel_width(int nb) { g_panel_width = nb > 0 ? (nb + PB - 1) / PB * PB : 0; }
 
+// ---- instrumentation for bench.py ------------------------------------------------------------------------
+void smnngp_instr_reset(int time_updates) {
+  instr_reset();
+  instr().time_updates = time_updates != 0;
+}
+long long smnngp_instr_launches(void) { return instr().launches; }
+int smnngp_instr_updates(double* total_ms, double* alg_flops) {
+  int n = 0;
+  double ms = instr_collect_update_ms(&n);
+  if (total_ms) *total_ms = ms;
+  if (alg_flops) *alg_flops = instr().update_alg_flops;
+  return n;
+}
+double smnngp_dmma_peak_tflops(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1.0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1.0;
+  return dmma_peak_tflops(sms);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 size_t smnngp_gram_workspace_bytes(int64_t N, int64_t M, int n_hidden, int arch) {
   Carver c(nullptr);
@@ -268,6 +288,7 @@ int smnngp_cov_solve_f64(void* stream, const double* cov, int64_t N, int64_t ld,
   CU(cudaMemsetAsync(scal, 0, SC_COUNT * sizeof(double), s));
   dim3 grid((unsigned)((N + 255) / 256 < 64 ? (N + 255) / 256 : 64), (unsigned)N);
   scale_shift_copy_kernel<<<grid, 256, 0, s>>>(cov, ld, A, lda, N, scale, shift);
+  instr().launches++;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(A + N * lda, y, N * sizeof(double), cudaMemcpyDeviceToDevice, s));
   CU(potrf_trapezoid(s, A, lda, N + 1, N, pick_nb(N), linv, scal + SC_LOGDET, info_dev));
@@ -332,6 +353,7 @@ static int predict_enqueue(cudaStream_t s, const double* X, const double* Y, con
     long long total = N * C;
     transpose_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Y, N, (int)C, w.A + (N + T) * w.lda,
                                                                            w.lda);
+    instr().launches++;
     CU(cudaGetLastError());
   }
   CU(potrf_trapezoid(s, w.A, w.lda, N + T + C, N, pick_nb(N), w.linv, w.scal + SC_LOGDET, info_dev));

@@ -67,6 +67,7 @@ cudaError_t launch_gemm_t(cudaStream_t s, const GemmParams& p) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)tiles, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(p);
+  instr().launches++;
   return cudaGetLastError();
 }
 
@@ -297,6 +298,7 @@ cudaError_t launch_potf2_trtri(cudaStream_t s, double* A, long long lda, int w, 
                                        PF_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   potf2_trtri_kernel<<<1, PF_THREADS, PF_SMEM_BYTES, s>>>(A, lda, w, Linv, logdet, info, global_col0);
+  instr().launches++;
   return cudaGetLastError();
 }
 
@@ -337,7 +339,13 @@ cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long 
       u.B = A + c1 * lda + c0; u.ldb = lda;
       u.C = A + c1 * lda + c1; u.ldc = lda;
       u.M = (int)(Mtot - c1); u.N = (int)(N - c1); u.K = (int)(c1 - c0); u.lower = 1;
+      if (instr().time_updates) {
+        // algorithmic flops: lower triangle of the square part + the carried rows, 2 flop per MAC
+        const double nsq = (double)(N - c1), extra = (double)(Mtot - N);
+        instr_begin_update(s, (nsq * (nsq + 1.0) + 2.0 * extra * nsq) * (double)u.K);
+      }
       e = launch_gemm_sub(s, u);
+      if (instr().time_updates) instr_end_update(s);
       if (e != cudaSuccess) return e;
     }
   }

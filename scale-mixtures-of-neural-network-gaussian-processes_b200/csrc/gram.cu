@@ -197,6 +197,7 @@ cudaError_t launch_gram_t(cudaStream_t s, const GramParams& p, long long tiles) 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)tiles, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(p);
+  instr().launches++;
   return cudaGetLastError();
 }
 
@@ -208,11 +209,13 @@ cudaError_t launch_qtable(cudaStream_t s, const double* X, long long ldx, int N,
   int warps_per_block = 8;
   unsigned blocks = (unsigned)((N + warps_per_block - 1) / warps_per_block);
   qtable_kernel<<<blocks, warps_per_block * 32, 0, s>>>(X, ldx, N, D, n_hidden, act, arch, hp, tab, tab_ld, qfin);
+  instr().launches++;
   return cudaGetLastError();
 }
 
 cudaError_t launch_scalars(cudaStream_t s, const double* qfin, int N, const double* hp, double* scal) {
   scalars_kernel<<<1, 1024, 0, s>>>(qfin, N, hp, scal);
+  instr().launches++;
   return cudaGetLastError();
 }
 

@@ -73,4 +73,20 @@ cudaError_t launch_test_nll_finalize(cudaStream_t s, const double* mean, const d
                                      double* nll_out);
 cudaError_t launch_fill_nan_if_bad(cudaStream_t s, const int* info, double* buf, long long n);
 
+// ---- instrumentation (bench.py): kernel-launch counter and CUDA-event timing of the trailing updates -------
+struct Instrumentation {
+  long long launches = 0;          // kernels of this library enqueued since the last reset
+  bool time_updates = false;       // record an event pair around every outer trailing update
+  double update_flops = 0.0;       // algorithmic flops of the timed trailing updates (executed lower tiles)
+  double update_alg_flops = 0.0;   // m*(n)*k style algorithmic count (lower triangle only, 2 flop / MAC)
+};
+Instrumentation& instr();
+void instr_begin_update(cudaStream_t s, double alg_flops);
+void instr_end_update(cudaStream_t s);
+// returns total milliseconds of the recorded trailing updates (synchronises on the events), count via n_out
+double instr_collect_update_ms(int* n_out);
+void instr_reset();
+// register-resident DMMA.8x8x4 issue-rate probe: returns TFLOP/s (synchronous; measurement tool)
+double dmma_peak_tflops(int device_sms);
+
 }  // namespace smnngp

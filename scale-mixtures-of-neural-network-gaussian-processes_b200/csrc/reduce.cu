@@ -145,12 +145,14 @@ __global__ void fill_nan_if_bad_kernel(const int* __restrict__ info, double* __r
 
 cudaError_t launch_sumsq(cudaStream_t s, const double* z, long long n, double* out) {
   sumsq_kernel<<<1, 1024, 0, s>>>(z, n, out);
+  instr().launches++;
   return cudaGetLastError();
 }
 
 cudaError_t launch_lml_finalize(cudaStream_t s, const double* scal, const double* hp, int kind, long long N,
                                 const int* info, double* out) {
   lml_finalize_kernel<<<1, 1, 0, s>>>(scal, hp, kind, N, info, out);
+  instr().launches++;
   return cudaGetLastError();
 }
 
@@ -159,6 +161,7 @@ cudaError_t launch_predict_finalize(cudaStream_t s, const double* V, long long l
                                     const int* info, double* mean, double* var) {
   if (T <= 0) return cudaSuccess;
   predict_finalize_kernel<<<T, 256, 0, s>>>(V, ldv, Z, ldz, ktt, C, N, info, mean, var);
+  instr().launches++;
   return cudaGetLastError();
 }
 
@@ -168,6 +171,7 @@ cudaError_t launch_test_nll_finalize(cudaStream_t s, const double* mean, const d
                                      double* nll_out) {
   test_nll_finalize_kernel<<<1, 1024, 0, s>>>(mean, var, ytest, T, N, y_mean, y_std, hp, kind, quad2, info, logp,
                                               nll_out);
+  instr().launches++;
   return cudaGetLastError();
 }
 
@@ -176,7 +180,96 @@ cudaError_t launch_fill_nan_if_bad(cudaStream_t s, const int* info, double* buf,
   long long blocks = (n + 255) / 256;
   if (blocks > 1184) blocks = 1184;
   fill_nan_if_bad_kernel<<<(unsigned)blocks, 256, 0, s>>>(info, buf, n);
+  instr().launches++;
   return cudaGetLastError();
+}
+
+
+// ---- instrumentation ---------------------------------------------------------------------------------------
+namespace {
+Instrumentation g_instr;
+struct EvPair { cudaEvent_t a, b; };
+EvPair g_ev[4096];
+int g_ev_made = 0, g_ev_used = 0;
+
+template <int NACC>
+__global__ void dmma_peak_kernel(double* out, int iters, double seed) {
+  double c[NACC][2];
+#pragma unroll
+  for (int i = 0; i < NACC; i++) c[i][0] = c[i][1] = 0.0;
+  double a = seed + threadIdx.x * 1e-9, b = seed - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < NACC; i++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < NACC; i++) s += c[i][0] + c[i][1];
+  if (s == 123.456) out[0] = s;
+}
+}  // namespace
+
+Instrumentation& instr() { return g_instr; }
+
+void instr_reset() {
+  g_instr.launches = 0;
+  g_instr.update_flops = 0.0;
+  g_instr.update_alg_flops = 0.0;
+  g_ev_used = 0;
+}
+
+void instr_begin_update(cudaStream_t s, double alg_flops) {
+  if (g_ev_used >= 4096) return;
+  if (g_ev_used >= g_ev_made) {
+    cudaEventCreate(&g_ev[g_ev_made].a);
+    cudaEventCreate(&g_ev[g_ev_made].b);
+    g_ev_made++;
+  }
+  g_instr.update_alg_flops += alg_flops;
+  cudaEventRecord(g_ev[g_ev_used].a, s);
+}
+
+void instr_end_update(cudaStream_t s) {
+  if (g_ev_used >= g_ev_made) return;
+  cudaEventRecord(g_ev[g_ev_used].b, s);
+  g_ev_used++;
+}
+
+double instr_collect_update_ms(int* n_out) {
+  double total = 0.0;
+  for (int i = 0; i < g_ev_used; i++) {
+    cudaEventSynchronize(g_ev[i].b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_ev[i].a, g_ev[i].b) == cudaSuccess) total += ms;
+  }
+  if (n_out) *n_out = g_ev_used;
+  return total;
+}
+
+double dmma_peak_tflops(int sms) {
+  double* d = nullptr;
+  if (cudaMalloc(&d, 64) != cudaSuccess) return -1.0;
+  const int iters = 20000, threads = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < 4; r++) {
+    cudaEventRecord(e0);
+    dmma_peak_kernel<16><<<sms, threads>>>(d, iters, 1.0);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  const double flop = 2.0 * 8 * 8 * 4 * 16.0 * iters * (threads / 32) * sms;
+  return flop / best * 1e-9;
 }
 
 }  // namespace smnngp
