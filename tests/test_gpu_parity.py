@@ -252,3 +252,28 @@ def test_medium_lml_pixel_shape(sm):
                               hp=hpd)
     assert int(info.item()) == 0
     assert abs(out[1].item() - ref) <= LML_TOL * abs(ref)
+
+
+def test_golden_vectors_on_gpu(sm):
+    """The committed mpmath fixtures (tests/golden/make_golden.py), CUDA path directly against them."""
+    import os
+    import torch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nngp_golden.npz"))
+    x, xt, y, yt = (torch.from_numpy(g[k]).cuda() for k in ("x", "xt", "y", "yt"))
+    eps, a, b = float(g["eps"]), float(g["a"]), float(g["b"])
+    for vi, s in enumerate(g["variants"]):
+        act, arch, L, w, bs, v = str(s).split(",")
+        spec = sm.StackSpec(int(L), act, arch)
+        hpd = sm.make_hp(float(w), float(bs), float(v), eps, a, b)
+        K = sm.device.gram(x, spec=spec, hp=hpd).cpu().numpy()
+        assert np.abs(K - g[f"K{vi}"]).max() <= GRAM_TOL * np.abs(K).max()
+        Ktd = sm.device.gram(xt, x, spec=spec, hp=hpd).cpu().numpy()
+        assert np.abs(Ktd - g[f"Ktd{vi}"]).max() <= GRAM_TOL * np.abs(K).max()
+        for kind, key in (("student_t", "t"), ("gauss", "g")):
+            out, info = sm.device.lml(x, y, spec=spec, hp=hpd, kind=kind)
+            assert abs(out[1].item() - float(g[f"loss_{key}{vi}"])) <= LML_TOL * abs(float(g[f"loss_{key}{vi}"]))
+            nll, mean, var, info = sm.device.test_nll(x, y, xt, yt, float(g["y_mean"]), float(g["y_std"]), spec=spec,
+                                                      hp=hpd, kind=kind)
+            assert np.abs(mean.cpu().numpy() - g[f"mean{vi}"]).max() <= LML_TOL * np.abs(g[f"mean{vi}"]).max()
+            assert np.abs(var.cpu().numpy() - g[f"var{vi}"]).max() <= LML_TOL * np.abs(g[f"var{vi}"]).max()
+            assert abs(nll.item() - float(g[f"nll_{key}{vi}"])) <= LML_TOL * abs(float(g[f"nll_{key}{vi}"]))
