@@ -118,6 +118,10 @@ void smnngp_host_release(void);
 
 /* tuning knob: outer panel width of the Cholesky (multiple of 128; 0 = automatic) */
 void smnngp_set_panel_width(int nb);
+/* tuning knob: CTA tile of the GEMM core. 0 = 128x64, two CTAs per SM (default); 1 = 128x128, one CTA per SM */
+void smnngp_set_tile_variant(int v);
+/* resident CTAs per SM of the update kernel for a tile variant (diagnostic) */
+int smnngp_debug_occupancy(int variant);
 
 /* ---- instrumentation (bench.py; no reference counterpart): kernel-launch counter, CUDA-event timing of the
  * Cholesky trailing updates (the dominant kernel) and a register-resident DMMA.8x8x4 issue-rate probe that

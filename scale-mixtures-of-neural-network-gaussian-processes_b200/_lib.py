@@ -24,7 +24,7 @@ EXPORTS = [
     "smnngp_cov_solve_workspace_bytes", "smnngp_cov_solve_f64",
     "smnngp_lml_workspace_bytes", "smnngp_lml_f64", "smnngp_predict_workspace_bytes", "smnngp_predict_f64",
     "smnngp_test_nll_f64", "smnngp_lml_host_f64", "smnngp_predict_host_f64", "smnngp_test_nll_host_f64",
-    "smnngp_host_release", "smnngp_set_panel_width",
+    "smnngp_host_release", "smnngp_set_panel_width", "smnngp_set_tile_variant", "smnngp_debug_occupancy",
     "smnngp_instr_reset", "smnngp_instr_launches", "smnngp_instr_updates", "smnngp_dmma_peak_tflops",
 ]
 
@@ -109,6 +109,9 @@ def _declare(lib):
     lib.smnngp_host_release.restype = None
     lib.smnngp_set_panel_width.restype = None
     lib.smnngp_set_panel_width.argtypes = [_i]
+    lib.smnngp_set_tile_variant.restype = None
+    lib.smnngp_set_tile_variant.argtypes = [_i]
+    lib.smnngp_debug_occupancy.argtypes = [_i]
     lib.smnngp_instr_reset.restype = None
     lib.smnngp_instr_reset.argtypes = [_i]
     lib.smnngp_instr_launches.restype = C.c_longlong

@@ -15,20 +15,62 @@ namespace {
 
 constexpr int EPI_STORE = 0, EPI_SUB = 1;
 
-template <bool ALIGN16, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const GemmParams p) {
+template <typename Cfg, bool ALIGN16, int EPI>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS) gemm_kernel(const GemmParams p) {
   extern __shared__ __align__(16) double smem[];
-  const int ntn = (p.N + BN - 1) / BN;
+  const int ntn = (p.N + Cfg::BN - 1) / Cfg::BN;
   int ti, tj;
-  decode_tile(blockIdx.x, ntn, p.lower, ti, tj);
-  const int r0 = ti * BM, c0 = tj * BN;
-  double acc[MI][NI][2];
-  gemm_mainloop<ALIGN16>(acc, p.A + (long long)r0 * p.lda, p.lda, min(BM, p.M - r0),
-                         p.B + (long long)c0 * p.ldb, p.ldb, min(BN, p.N - c0), p.K, smem);
+  decode_tile<Cfg::Q>(blockIdx.x, ntn, p.lower, ti, tj);
+  const int r0 = ti * Cfg::BM, c0 = tj * Cfg::BN;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rbase = r0 + (warp >> 2) * 64 + (lane >> 2);
-  const int cbase = c0 + (warp & 3) * 32 + (lane & 3) * 2;
+  const int rbase = r0 + (warp / Cfg::WARPS_N) * 64 + (lane >> 2);
+  const int cbase = c0 + (warp % Cfg::WARPS_N) * 32 + (lane & 3) * 2;
+  double* __restrict__ Cg = p.C;
+  if (EPI == EPI_SUB) {
+    // pull this thread's part of the C tile towards L2 while the contraction runs (no registers held)
+#pragma unroll
+    for (int mi = 0; mi < MI; mi++) {
+      const int r = rbase + mi * 8;
+      if (r < p.M && cbase < p.N && (lane & 3) == 0)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(Cg + (long long)r * p.ldc + cbase));
+    }
+  }
+  double acc[MI][NI][2];
+  gemm_mainloop<Cfg, ALIGN16>(acc, p.A + (long long)r0 * p.lda, p.lda, min(Cfg::BM, p.M - r0),
+                              p.B + (long long)c0 * p.ldb, p.ldb, min(Cfg::BN, p.N - c0), p.K, smem);
   const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+  // tile fully inside the matrix and (if masked) fully below the diagonal: batched 16-byte read-modify-write
+  const bool interior = vec_ok && (r0 + Cfg::BM <= p.M) && (c0 + Cfg::BN <= p.N) &&
+                        (!p.lower || c0 + Cfg::BN - 1 <= r0);
+  if (interior) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      double2 cv[MI / 2][NI];
+      if (EPI == EPI_SUB) {
+#pragma unroll
+        for (int m = 0; m < MI / 2; m++)
+#pragma unroll
+          for (int ni = 0; ni < NI; ni++)
+            cv[m][ni] = *reinterpret_cast<const double2*>(
+                Cg + (long long)(rbase + (half * (MI / 2) + m) * 8) * p.ldc + cbase + ni * 8);
+      }
+#pragma unroll
+      for (int m = 0; m < MI / 2; m++)
+#pragma unroll
+        for (int ni = 0; ni < NI; ni++) {
+          const int mi = half * (MI / 2) + m;
+          double2 v;
+          if (EPI == EPI_SUB) {
+            v.x = cv[m][ni].x - acc[mi][ni][0];
+            v.y = cv[m][ni].y - acc[mi][ni][1];
+          } else {
+            v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+          }
+          *reinterpret_cast<double2*>(Cg + (long long)(rbase + mi * 8) * p.ldc + cbase + ni * 8) = v;
+        }
+    }
+    return;
+  }
 #pragma unroll
   for (int mi = 0; mi < MI; mi++) {
     const int r = rbase + mi * 8;
@@ -38,7 +80,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const GemmParams 
       const int c = cbase + ni * 8;
       const bool ok0 = c < p.N && (!p.lower || c <= r);
       const bool ok1 = (c + 1) < p.N && (!p.lower || (c + 1) <= r);
-      double* dst = p.C + (long long)r * p.ldc + c;
+      double* dst = Cg + (long long)r * p.ldc + c;
       if (ok0 && ok1 && vec_ok) {
         double2* d2 = reinterpret_cast<double2*>(dst);
         if (EPI == EPI_STORE) {
@@ -57,18 +99,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const GemmParams 
   }
 }
 
+template <typename Cfg, int EPI>
+cudaError_t launch_gemm_cfg(cudaStream_t s, const GemmParams& p) {
+  long long tiles = count_tiles<Cfg>(p.M, p.N, p.lower);
+  bool a16 = (p.lda % 2 == 0) && (p.ldb % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) &&
+             ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
+  auto kern = a16 ? gemm_kernel<Cfg, true, EPI> : gemm_kernel<Cfg, false, EPI>;
+  static bool configured[2] = {false, false};
+  if (!configured[a16]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    configured[a16] = true;
+  }
+  kern<<<(unsigned)tiles, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
+  instr().launches++;
+  return cudaGetLastError();
+}
+
 template <int EPI>
 cudaError_t launch_gemm_t(cudaStream_t s, const GemmParams& p) {
   if (p.M <= 0 || p.N <= 0) return cudaSuccess;
-  long long tiles = count_tiles(p.M, p.N, p.lower);
-  bool a16 = (p.lda % 2 == 0) && (p.ldb % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) &&
-             ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
-  auto kern = a16 ? gemm_kernel<true, EPI> : gemm_kernel<false, EPI>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  kern<<<(unsigned)tiles, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(p);
-  instr().launches++;
-  return cudaGetLastError();
+  return tile_variant() == 1 ? launch_gemm_cfg<TileBig, EPI>(s, p) : launch_gemm_cfg<TilePair, EPI>(s, p);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -288,6 +341,22 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
 }
 
 }  // namespace
+
+int debug_gemm_occupancy(int variant) {
+  int nb = -1;
+  if (variant == 1) {
+    auto k = gemm_kernel<TileBig, true, EPI_SUB>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TileBig::SMEM_BYTES);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, TileBig::THREADS, TileBig::SMEM_BYTES);
+  } else {
+    auto k = gemm_kernel<TilePair, true, EPI_SUB>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TilePair::SMEM_BYTES);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, TilePair::THREADS, TilePair::SMEM_BYTES);
+  }
+  return nb;
+}
 
 cudaError_t launch_gemm_store(cudaStream_t s, const GemmParams& p) { return launch_gemm_t<EPI_STORE>(s, p); }
 cudaError_t launch_gemm_sub(cudaStream_t s, const GemmParams& p) { return launch_gemm_t<EPI_SUB>(s, p); }

@@ -8,16 +8,26 @@
 
 namespace smnngp {
 
-constexpr int BM = 128;          // CTA tile rows
-constexpr int BN = 128;          // CTA tile cols
 constexpr int BK = 16;           // k-slab per pipeline stage
 constexpr int LDK = BK + 4;      // padded smem row (doubles): 160 B rows -> conflict-free 8-row x 4-k fragment loads
-constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 256;  // 8 warps as 2 (M) x 4 (N); warp tile 64 x 32
-constexpr int STAGE_DOUBLES = (BM + BN) * LDK;
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;  // 163840
-constexpr int MI = 8;            // m8 blocks per warp tile
+constexpr int MI = 8;            // m8 blocks per warp tile (warp tile = 64 x 32)
 constexpr int NI = 4;            // n8 blocks per warp tile
+
+// CTA tile configuration of the GEMM core.  Warp tile is fixed at 64 x 32 (64 FP64 accumulators per thread).
+//   TilePair: 128 x 64, 4 warps, 90 KB ring -> TWO CTAs per SM: while one CTA is in its prologue / epilogue the
+//             other one owns the FP64 pipe (ping-pong), which is what keeps DMMA issue saturated;
+//   TileBig : 128 x 128, 8 warps, 160 KB ring, one CTA per SM (round-1 first version, kept for comparison).
+template <int BM_, int BN_, int STAGES_, int MINB_>
+struct TileCfg {
+  static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_, MIN_BLOCKS = MINB_;
+  static constexpr int WARPS_M = BM / 64, WARPS_N = BN / 32;
+  static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+  static constexpr int STAGE_DOUBLES = (BM + BN) * LDK;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
+  static constexpr int Q = BM / BN;    // column tiles per row tile on the diagonal
+};
+using TilePair = TileCfg<128, 64, 3, 2>;   // 3 x 30 KB (padded) = 90 KB -> two CTAs fit in 228 KB
+using TileBig = TileCfg<128, 128, 4, 1>;
 
 enum Act { ACT_RELU = 0, ACT_ERF = 1 };
 enum Arch { ARCH_MLP = 0, ARCH_RESNET = 1 };
@@ -53,36 +63,38 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// Linear tile id -> (ti, tj).  lower != 0: only tiles with tj <= ti (region starts on the diagonal; rows may
-// extend past the column count = trapezoid).  ntn = number of column tiles.
+// Linear tile id -> (ti, tj).  lower != 0: only tiles that contain an element with col <= row (the region
+// starts on the diagonal; rows may extend past the column count = trapezoid).  With BM = Q*BN row tile r owns
+// min(ntn, Q*r + Q) column tiles.  ntn = number of column tiles.
+template <int Q>
 __device__ __forceinline__ void decode_tile(long long t, int ntn, int lower, int& ti, int& tj) {
   if (!lower) {
     ti = (int)(t / ntn);
     tj = (int)(t % ntn);
     return;
   }
-  long long tri = (long long)ntn * (ntn + 1) / 2;
+  const long long r0 = ntn / Q;                   // rows 0..r0-1 are strictly triangular
+  const long long tri = Q * r0 * (r0 + 1) / 2;
   if (t < tri) {
-    long long r = (long long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while (r * (r + 1) / 2 > t) --r;
-    while ((r + 1) * (r + 2) / 2 <= t) ++r;
+    long long r = (long long)((sqrt(8.0 * (double)t / (double)Q + 1.0) - 1.0) * 0.5);
+    while (Q * r * (r + 1) / 2 > t) --r;
+    while (Q * (r + 1) * (r + 2) / 2 <= t) ++r;
     ti = (int)r;
-    tj = (int)(t - r * (r + 1) / 2);
+    tj = (int)(t - Q * r * (r + 1) / 2);
   } else {
     long long u = t - tri;
-    ti = ntn + (int)(u / ntn);
+    ti = (int)(r0 + u / ntn);
     tj = (int)(u % ntn);
   }
 }
 
+template <typename Cfg>
 static inline long long count_tiles(long long M, long long N, int lower) {
-  long long ntm = (M + BM - 1) / BM, ntn = (N + BN - 1) / BN;
+  const long long ntm = (M + Cfg::BM - 1) / Cfg::BM, ntn = (N + Cfg::BN - 1) / Cfg::BN;
   if (!lower) return ntm * ntn;
-  long long sq = ntm < ntn ? ntm : ntn;
-  long long tri = sq * (sq + 1) / 2;
-  // rows beyond the square part see all column tiles; (ntm < ntn cannot happen for our regions but stay safe)
-  if (ntm >= ntn) return ntn * (ntn + 1) / 2 + (ntm - ntn) * ntn;
-  return tri;
+  const long long r0 = ntn / Cfg::Q;
+  if (ntm <= r0) return Cfg::Q * ntm * (ntm + 1) / 2;
+  return Cfg::Q * r0 * (r0 + 1) / 2 + (ntm - r0) * ntn;
 }
 
 }  // namespace smnngp

@@ -8,17 +8,17 @@
 namespace smnngp {
 
 // Per-thread addressing of the cp.async staging, hoisted out of the k loop.  Each thread copies the same
-// (row, k-chunk) slots of every slab: 4 x 16 B (aligned operands) or 8 x 8 B.
-template <bool ALIGN16>
+// (row, k-chunk) slots of every slab: 16-byte chunks (aligned operands) or 8-byte chunks.
+template <bool ALIGN16, int ROWS, int THREADS>
 struct TileLoader {
-  static constexpr int NCH = ALIGN16 ? 4 : 8;
+  static constexpr int NCH = ROWS * (ALIGN16 ? 8 : 16) / THREADS;
   const double* src[NCH];   // global address of the slot at k0 = 0 (nullptr: row out of range -> always zero fill)
   int soff[NCH];            // smem offset (doubles) inside the operand tile
   int kc[NCH];              // k offset of the slot inside a slab
   __device__ __forceinline__ void init(const double* __restrict__ g, long long ld, int rows_valid, int tid) {
 #pragma unroll
     for (int i = 0; i < NCH; i++) {
-      int c = tid + i * GEMM_THREADS;
+      int c = tid + i * THREADS;
       int r = ALIGN16 ? (c >> 3) : (c >> 4);
       kc[i] = ALIGN16 ? (c & 7) * 2 : (c & 15);
       soff[i] = r * LDK + kc[i];
@@ -38,29 +38,31 @@ struct TileLoader {
   }
 };
 
-// Accumulator element acc[mi][ni][e] is C(row, col) with
-//   row = wm*64 + mi*8 + (lane>>2),  col = wn*32 + ni*8 + (lane&3)*2 + e      (wm = warp>>2, wn = warp&3)
-template <bool ALIGN16>
+// Accumulator element acc[mi][ni][e] is C(row, col) of the CTA tile with
+//   row = wm*64 + mi*8 + (lane>>2),  col = wn*32 + ni*8 + (lane&3)*2 + e   (wm = warp / WARPS_N, wn = warp % WARPS_N)
+template <typename Cfg, bool ALIGN16>
 __device__ __forceinline__ void gemm_mainloop(double (&acc)[MI][NI][2], const double* __restrict__ Ag,
                                               long long lda, int a_rows, const double* __restrict__ Bg,
                                               long long ldb, int b_rows, int K, double* smem) {
+  constexpr int STAGES = Cfg::STAGES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
+  const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
   const int KT = (K + BK - 1) / BK;
 #pragma unroll
   for (int mi = 0; mi < MI; mi++)
 #pragma unroll
     for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-  TileLoader<ALIGN16> la, lb;
+  TileLoader<ALIGN16, Cfg::BM, Cfg::THREADS> la;
+  TileLoader<ALIGN16, Cfg::BN, Cfg::THREADS> lb;
   la.init(Ag, lda, a_rows, tid);
   lb.init(Bg, ldb, b_rows, tid);
 #pragma unroll
   for (int s = 0; s < STAGES - 1; s++) {
     if (s < KT) {
-      double* st = smem + s * STAGE_DOUBLES;
+      double* st = smem + s * Cfg::STAGE_DOUBLES;
       la.issue(st, s * BK, K, Ag);
-      lb.issue(st + BM * LDK, s * BK, K, Bg);
+      lb.issue(st + Cfg::BM * LDK, s * BK, K, Bg);
     }
     cp_async_commit();
   }
@@ -68,9 +70,9 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[MI][NI][2], const do
   for (int kt = 0; kt < KT; kt++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    const double* As = smem + (kt % STAGES) * STAGE_DOUBLES;
+    const double* As = smem + (kt % STAGES) * Cfg::STAGE_DOUBLES;
     const double* ap = As + (wm * 64) * LDK + frag_off;
-    const double* bp = As + BM * LDK + (wn * 32) * LDK + frag_off;
+    const double* bp = As + Cfg::BM * LDK + (wn * 32) * LDK + frag_off;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; kk++) {
       double a[MI], b[NI];
@@ -87,9 +89,9 @@ __device__ __forceinline__ void gemm_mainloop(double (&acc)[MI][NI][2], const do
         // tensor pipe is already busy while the copy instructions go out
         int nk = kt + STAGES - 1;
         if (nk < KT) {
-          double* st = smem + (nk % STAGES) * STAGE_DOUBLES;
+          double* st = smem + (nk % STAGES) * Cfg::STAGE_DOUBLES;
           la.issue(st, nk * BK, K, Ag);
-          lb.issue(st + BM * LDK, nk * BK, K, Bg);
+          lb.issue(st + Cfg::BM * LDK, nk * BK, K, Bg);
         }
         cp_async_commit();
       }

@@ -93,26 +93,25 @@ __global__ void scalars_kernel(const double* __restrict__ qfin, int N, const dou
   }
 }
 
-template <bool ALIGN16, int ACT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gram_kernel(const GramParams p) {
+template <typename Cfg, bool ALIGN16, int ACT>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS) gram_kernel(const GramParams p) {
   extern __shared__ __align__(16) double smem[];
-  const int ntn = (p.M + BN - 1) / BN;
+  const int ntn = (p.M + Cfg::BN - 1) / Cfg::BN;
   int ti, tj;
-  decode_tile(blockIdx.x, ntn, p.symmetric, ti, tj);
-  const int r0 = ti * BM, c0 = tj * BN;
+  decode_tile<Cfg::Q>(blockIdx.x, ntn, p.symmetric, ti, tj);
+  const int r0 = ti * Cfg::BM, c0 = tj * Cfg::BN;
   double acc[MI][NI][2];
-  gemm_mainloop<ALIGN16>(acc, p.X1 + (long long)r0 * p.ld1, p.ld1, min(BM, p.N - r0),
-                         p.X2 + (long long)c0 * p.ld2, p.ld2, min(BN, p.M - c0), p.D, smem);
+  gemm_mainloop<Cfg, ALIGN16>(acc, p.X1 + (long long)r0 * p.ld1, p.ld1, min(Cfg::BM, p.N - r0),
+                              p.X2 + (long long)c0 * p.ld2, p.ld2, min(Cfg::BN, p.M - c0), p.D, smem);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rbase = r0 + (warp >> 2) * 64 + (lane >> 2);
-  const int cbase = c0 + (warp & 3) * 32 + (lane & 3) * 2;
+  const int rbase = r0 + (warp / Cfg::WARPS_N) * 64 + (lane >> 2);
+  const int cbase = c0 + (warp % Cfg::WARPS_N) * 32 + (lane & 3) * 2;
   const double w2 = p.hp[HP_W] * p.hp[HP_W], b2 = p.hp[HP_B] * p.hp[HP_B], v2 = p.hp[HP_V] * p.hp[HP_V];
-  const bool diag_tile = p.symmetric && (ti == tj);
   const double dD = (double)p.D;
   const bool resnet = p.arch == ARCH_RESNET;
 
-  // which of this thread's 64 entries are real output (edge tiles, strict upper part of diagonal tiles)
+  // which of this thread's 64 entries are real output (edge tiles, strict upper part on the symmetric path)
   unsigned long long live = 0ull;
 #pragma unroll
   for (int mi = 0; mi < MI; mi++)
@@ -121,7 +120,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_kernel(const GramParams 
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         int r = rbase + mi * 8, c = cbase + ni * 8 + e;
-        bool ok = r < p.N && c < p.M && (!diag_tile || c <= r);
+        bool ok = r < p.N && c < p.M && (!p.symmetric || c <= r);
         if (ok) live |= 1ull << (mi * 8 + ni * 2 + e);
         double k = acc[mi][ni][e] / dD;                 // kernel_fn normalises X.X'^T by the feature count
         acc[mi][ni][e] = resnet ? (w2 * k + b2) : k;    // dense-resnet: leading Dense(512)
@@ -159,7 +158,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_kernel(const GramParams 
 
   const double sh = (p.symmetric && p.shift != SHIFT_NONE) ? p.scal[SC_SHIFT0 + p.shift] : 0.0;
   const bool vec_ok = ((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15) == 0);
-  const bool mirror = p.symmetric && p.out_full && !diag_tile;
+  const bool mirror = p.symmetric && p.out_full;
 #pragma unroll
   for (int mi = 0; mi < MI; mi++) {
     const int r = rbase + mi * 8;
@@ -181,9 +180,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_kernel(const GramParams 
         if (ok1) dst[1] = k1;
       }
       if (mirror) {
-        if (ok0) p.K[(long long)c * p.ldk + r] = k0;
-        if (ok1) p.K[(long long)(c + 1) * p.ldk + r] = k1;
-      } else if (diag_tile && p.out_full) {
         if (ok0 && c != r) p.K[(long long)c * p.ldk + r] = k0;
         if (ok1 && c + 1 != r) p.K[(long long)(c + 1) * p.ldk + r] = k1;
       }
@@ -191,12 +187,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_kernel(const GramParams 
   }
 }
 
-template <bool ALIGN16>
-cudaError_t launch_gram_t(cudaStream_t s, const GramParams& p, long long tiles) {
-  auto kern = p.act == ACT_RELU ? gram_kernel<ALIGN16, ACT_RELU> : gram_kernel<ALIGN16, ACT_ERF>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+template <typename Cfg, bool ALIGN16>
+cudaError_t launch_gram_t(cudaStream_t s, const GramParams& p) {
+  long long tiles = count_tiles<Cfg>(p.N, p.M, p.symmetric);
+  auto kern = p.act == ACT_RELU ? gram_kernel<Cfg, ALIGN16, ACT_RELU> : gram_kernel<Cfg, ALIGN16, ACT_ERF>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  kern<<<(unsigned)tiles, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(p);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)tiles, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
   instr().launches++;
   return cudaGetLastError();
 }
@@ -221,10 +220,10 @@ cudaError_t launch_scalars(cudaStream_t s, const double* qfin, int N, const doub
 
 cudaError_t launch_gram(cudaStream_t s, const GramParams& p) {
   if (p.N <= 0 || p.M <= 0) return cudaSuccess;
-  long long tiles = count_tiles(p.N, p.M, p.symmetric);
   bool a16 = (p.ld1 % 2 == 0) && (p.ld2 % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.X1) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(p.X2) & 15) == 0);
-  return a16 ? launch_gram_t<true>(s, p, tiles) : launch_gram_t<false>(s, p, tiles);
+  if (tile_variant() == 1) return a16 ? launch_gram_t<TileBig, true>(s, p) : launch_gram_t<TileBig, false>(s, p);
+  return a16 ? launch_gram_t<TilePair, true>(s, p) : launch_gram_t<TilePair, false>(s, p);
 }
 
 }  // namespace smnngp

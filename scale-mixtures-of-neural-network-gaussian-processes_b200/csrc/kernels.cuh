@@ -7,6 +7,10 @@ namespace smnngp {
 constexpr int HP_W = 0, HP_B = 1, HP_V = 2, HP_EPS = 3, HP_ALPHA = 4, HP_BETA = 5, HP_COUNT = 6;
 constexpr int PB = 128;  // diagonal block / inner panel width of the Cholesky
 
+// 0 = TilePair (128x64, two CTAs per SM; default), 1 = TileBig (128x128, one CTA per SM)
+int& tile_variant();
+int debug_gemm_occupancy(int variant);
+
 inline int n_act_applications(int n_hidden, int arch) { return arch == ARCH_RESNET ? n_hidden + 1 : n_hidden; }
 
 struct GramParams {

@@ -213,6 +213,11 @@ __global__ void dmma_peak_kernel(double* out, int iters, double seed) {
 
 Instrumentation& instr() { return g_instr; }
 
+int& tile_variant() {
+  static int v = 0;
+  return v;
+}
+
 void instr_reset() {
   g_instr.launches = 0;
   g_instr.update_flops = 0.0;
