@@ -118,7 +118,8 @@ void smnngp_host_release(void);
 
 /* tuning knob: outer panel width of the Cholesky (multiple of 128; 0 = automatic) */
 void smnngp_set_panel_width(int nb);
-/* tuning knob: CTA tile of the GEMM core. 0 = 128x64, two CTAs per SM (default); 1 = 128x128, one CTA per SM */
+/* tuning knob: GEMM core. 0 = TMA-fed persistent ping-pong kernel (default; cp.async 128x64 for unaligned
+ * operands); 1 = cp.async 128x128, one CTA per SM; 2 = cp.async 128x64, two CTAs per SM */
 void smnngp_set_tile_variant(int v);
 /* resident CTAs per SM of the update kernel for a tile variant (diagnostic) */
 int smnngp_debug_occupancy(int variant);

@@ -147,7 +147,7 @@ int smnngp_abi_version(void) { return SMNNGP_ABI_VERSION; }
 const char* smnngp_last_error(void) { return g_err.c_str(); }
 void smnngp_set_panel_width(int nb) { g_panel_width = nb > 0 ? (nb + PB - 1) / PB * PB : 0; }
 
-void smnngp_set_tile_variant(int v) { tile_variant() = v == 1 ? 1 : 0; }
+void smnngp_set_tile_variant(int v) { tile_variant() = (v >= 0 && v <= 2) ? v : 0; }
 int smnngp_debug_occupancy(int variant) { return debug_gemm_occupancy(variant); }
 
 // ---- instrumentation for bench.py ------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 // fused into the factorisation and run on the tensor pipe.
 #include "gemm_core.cuh"
 #include "kernels.cuh"
+#include "tma_core.cuh"
 
 namespace smnngp {
 
@@ -15,33 +16,15 @@ namespace {
 
 constexpr int EPI_STORE = 0, EPI_SUB = 1;
 
-template <typename Cfg, bool ALIGN16, int EPI>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS) gemm_kernel(const GemmParams p) {
-  extern __shared__ __align__(16) double smem[];
-  const int ntn = (p.N + Cfg::BN - 1) / Cfg::BN;
-  int ti, tj;
-  decode_tile<Cfg::Q>(blockIdx.x, ntn, p.lower, ti, tj);
-  const int r0 = ti * Cfg::BM, c0 = tj * Cfg::BN;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rbase = r0 + (warp / Cfg::WARPS_N) * 64 + (lane >> 2);
-  const int cbase = c0 + (warp % Cfg::WARPS_N) * 32 + (lane & 3) * 2;
+// C (op)= acc for one warp's 64 x 32 part of a tile whose origin is (r0, c0) and size tile_bm x tile_bn.
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue(const GemmParams& p, double (&acc)[MI][NI][2], int r0, int c0,
+                                              int tile_bm, int tile_bn, int rbase, int cbase) {
   double* __restrict__ Cg = p.C;
-  if (EPI == EPI_SUB) {
-    // pull this thread's part of the C tile towards L2 while the contraction runs (no registers held)
-#pragma unroll
-    for (int mi = 0; mi < MI; mi++) {
-      const int r = rbase + mi * 8;
-      if (r < p.M && cbase < p.N && (lane & 3) == 0)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(Cg + (long long)r * p.ldc + cbase));
-    }
-  }
-  double acc[MI][NI][2];
-  gemm_mainloop<Cfg, ALIGN16>(acc, p.A + (long long)r0 * p.lda, p.lda, min(Cfg::BM, p.M - r0),
-                              p.B + (long long)c0 * p.ldb, p.ldb, min(Cfg::BN, p.N - c0), p.K, smem);
   const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
   // tile fully inside the matrix and (if masked) fully below the diagonal: batched 16-byte read-modify-write
-  const bool interior = vec_ok && (r0 + Cfg::BM <= p.M) && (c0 + Cfg::BN <= p.N) &&
-                        (!p.lower || c0 + Cfg::BN - 1 <= r0);
+  const bool interior = vec_ok && (r0 + tile_bm <= p.M) && (c0 + tile_bn <= p.N) &&
+                        (!p.lower || c0 + tile_bn - 1 <= r0);
   if (interior) {
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -99,6 +82,50 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS) gemm_kernel(con
   }
 }
 
+template <typename Cfg, bool ALIGN16, int EPI>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS) gemm_kernel(const GemmParams p) {
+  extern __shared__ __align__(16) double smem[];
+  const int ntn = (p.N + Cfg::BN - 1) / Cfg::BN;
+  int ti, tj;
+  decode_tile<Cfg::Q>(blockIdx.x, ntn, p.lower, ti, tj);
+  const int r0 = ti * Cfg::BM, c0 = tj * Cfg::BN;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rbase = r0 + (warp / Cfg::WARPS_N) * 64 + (lane >> 2);
+  const int cbase = c0 + (warp % Cfg::WARPS_N) * 32 + (lane & 3) * 2;
+  if (EPI == EPI_SUB) {
+    // pull this thread's part of the C tile towards L2 while the contraction runs (no registers held)
+#pragma unroll
+    for (int mi = 0; mi < MI; mi++) {
+      const int r = rbase + mi * 8;
+      if (r < p.M && cbase < p.N && (lane & 3) == 0)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.C + (long long)r * p.ldc + cbase));
+    }
+  }
+  double acc[MI][NI][2];
+  gemm_mainloop<Cfg, ALIGN16>(acc, p.A + (long long)r0 * p.lda, p.lda, min(Cfg::BM, p.M - r0),
+                              p.B + (long long)c0 * p.ldb, p.ldb, min(Cfg::BN, p.N - c0), p.K, smem);
+  gemm_epilogue<EPI>(p, acc, r0, c0, Cfg::BM, Cfg::BN, rbase, cbase);
+}
+
+// TMA-fed persistent variant (tma_core.cuh): trailing / inner updates C -= A B^T
+struct EpiSubTma {
+  using Params = GemmParams;
+  static __device__ __forceinline__ void apply(const Params& p, double (&acc)[MI][NI][2], int r0, int c0, int wm,
+                                               int wn, int lane) {
+    gemm_epilogue<EPI_SUB>(p, acc, r0, c0, TM_BM, TM_BN, r0 + wm * 64 + (lane >> 2), c0 + wn * 32 + (lane & 3) * 2);
+  }
+};
+
+cudaError_t launch_gemm_sub_tma(cudaStream_t s, const GemmParams& p) {
+  CUtensorMap ma, mb;
+  if (!make_tmap(&ma, p.A, p.M, p.K, p.lda, TM_BM) || !make_tmap(&mb, p.B, p.N, p.K, p.ldb, TM_BN))
+    return cudaErrorInvalidValue;
+  TmaShape sh{p.M, p.N, p.K, p.lower, count_tiles<TileTma>(p.M, p.N, p.lower)};
+  cudaError_t e = launch_tma_gemm<EpiSubTma>(s, ma, mb, sh, p, device_sm_count());
+  instr().launches++;
+  return e;
+}
+
 template <typename Cfg, int EPI>
 cudaError_t launch_gemm_cfg(cudaStream_t s, const GemmParams& p) {
   long long tiles = count_tiles<Cfg>(p.M, p.N, p.lower);
@@ -121,7 +148,11 @@ cudaError_t launch_gemm_cfg(cudaStream_t s, const GemmParams& p) {
 template <int EPI>
 cudaError_t launch_gemm_t(cudaStream_t s, const GemmParams& p) {
   if (p.M <= 0 || p.N <= 0) return cudaSuccess;
-  return tile_variant() == 1 ? launch_gemm_cfg<TileBig, EPI>(s, p) : launch_gemm_cfg<TilePair, EPI>(s, p);
+  // The TRSM runs IN PLACE (C aliases A): a CTA must own whole rows of the <= 128-column panel, otherwise one
+  // column tile could overwrite rows a sibling tile is still reading -> always the 128 x 128 tile for EPI_STORE.
+  if (EPI == EPI_STORE || tile_variant() == 1) return launch_gemm_cfg<TileBig, EPI>(s, p);
+  if (tile_variant() == 0 && tma_operand_ok(p.A, p.lda) && tma_operand_ok(p.B, p.ldb)) return launch_gemm_sub_tma(s, p);
+  return launch_gemm_cfg<TilePair, EPI>(s, p);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -4,6 +4,7 @@
 // HBM exactly once.  Symmetric case: only tiles on or below the diagonal are computed (optionally mirrored).
 #include "gemm_core.cuh"
 #include "kernels.cuh"
+#include "tma_core.cuh"
 
 namespace smnngp {
 
@@ -93,20 +94,9 @@ __global__ void scalars_kernel(const double* __restrict__ qfin, int N, const dou
   }
 }
 
-template <typename Cfg, bool ALIGN16, int ACT>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS) gram_kernel(const GramParams p) {
-  extern __shared__ __align__(16) double smem[];
-  const int ntn = (p.M + Cfg::BN - 1) / Cfg::BN;
-  int ti, tj;
-  decode_tile<Cfg::Q>(blockIdx.x, ntn, p.symmetric, ti, tj);
-  const int r0 = ti * Cfg::BM, c0 = tj * Cfg::BN;
-  double acc[MI][NI][2];
-  gemm_mainloop<Cfg, ALIGN16>(acc, p.X1 + (long long)r0 * p.ld1, p.ld1, min(Cfg::BM, p.N - r0),
-                              p.X2 + (long long)c0 * p.ld2, p.ld2, min(Cfg::BN, p.M - c0), p.D, smem);
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rbase = r0 + (warp / Cfg::WARPS_N) * 64 + (lane >> 2);
-  const int cbase = c0 + (warp % Cfg::WARPS_N) * 32 + (lane & 3) * 2;
+// L-layer recursion + final Dense + diagonal shift + store for one warp's 64 x 32 part of a tile
+template <int ACT>
+__device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)[MI][NI][2], int rbase, int cbase) {
   const double w2 = p.hp[HP_W] * p.hp[HP_W], b2 = p.hp[HP_B] * p.hp[HP_B], v2 = p.hp[HP_V] * p.hp[HP_V];
   const double dD = (double)p.D;
   const bool resnet = p.arch == ARCH_RESNET;
@@ -187,6 +177,42 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS) gram_kernel(con
   }
 }
 
+template <typename Cfg, bool ALIGN16, int ACT>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS) gram_kernel(const GramParams p) {
+  extern __shared__ __align__(16) double smem[];
+  const int ntn = (p.M + Cfg::BN - 1) / Cfg::BN;
+  int ti, tj;
+  decode_tile<Cfg::Q>(blockIdx.x, ntn, p.symmetric, ti, tj);
+  const int r0 = ti * Cfg::BM, c0 = tj * Cfg::BN;
+  double acc[MI][NI][2];
+  gemm_mainloop<Cfg, ALIGN16>(acc, p.X1 + (long long)r0 * p.ld1, p.ld1, min(Cfg::BM, p.N - r0),
+                              p.X2 + (long long)c0 * p.ld2, p.ld2, min(Cfg::BN, p.M - c0), p.D, smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  gram_epilogue<ACT>(p, acc, r0 + (warp / Cfg::WARPS_N) * 64 + (lane >> 2),
+                     c0 + (warp % Cfg::WARPS_N) * 32 + (lane & 3) * 2);
+}
+
+// TMA-fed persistent variant (tma_core.cuh)
+template <int ACT>
+struct EpiGramTma {
+  using Params = GramParams;
+  static __device__ __forceinline__ void apply(const Params& p, double (&acc)[MI][NI][2], int r0, int c0, int wm,
+                                               int wn, int lane) {
+    gram_epilogue<ACT>(p, acc, r0 + wm * 64 + (lane >> 2), c0 + wn * 32 + (lane & 3) * 2);
+  }
+};
+
+cudaError_t launch_gram_tma(cudaStream_t s, const GramParams& p) {
+  CUtensorMap ma, mb;
+  if (!make_tmap(&ma, p.X1, p.N, p.D, p.ld1, TM_BM) || !make_tmap(&mb, p.X2, p.M, p.D, p.ld2, TM_BN))
+    return cudaErrorInvalidValue;
+  TmaShape sh{p.N, p.M, p.D, p.symmetric, count_tiles<TileTma>(p.N, p.M, p.symmetric)};
+  cudaError_t e = p.act == ACT_RELU ? launch_tma_gemm<EpiGramTma<ACT_RELU>>(s, ma, mb, sh, p, device_sm_count())
+                                    : launch_tma_gemm<EpiGramTma<ACT_ERF>>(s, ma, mb, sh, p, device_sm_count());
+  instr().launches++;
+  return e;
+}
+
 template <typename Cfg, bool ALIGN16>
 cudaError_t launch_gram_t(cudaStream_t s, const GramParams& p) {
   long long tiles = count_tiles<Cfg>(p.N, p.M, p.symmetric);
@@ -223,6 +249,7 @@ cudaError_t launch_gram(cudaStream_t s, const GramParams& p) {
   bool a16 = (p.ld1 % 2 == 0) && (p.ld2 % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.X1) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(p.X2) & 15) == 0);
   if (tile_variant() == 1) return a16 ? launch_gram_t<TileBig, true>(s, p) : launch_gram_t<TileBig, false>(s, p);
+  if (tile_variant() == 0 && tma_operand_ok(p.X1, p.ld1) && tma_operand_ok(p.X2, p.ld2)) return launch_gram_tma(s, p);
   return a16 ? launch_gram_t<TilePair, true>(s, p) : launch_gram_t<TilePair, false>(s, p);
 }
 
