@@ -103,6 +103,32 @@ int smnngp_test_nll_f64(void* stream, const double* X, const double* y, const do
                         double* nll_out_dev, double* mean_out, double* var_out, double* logp_out,
                         int* info_dev);
 
+/* ---- stage-level entry points (multi-GPU driver: one process per GPU interleaves these with NCCL collectives;
+ * same kernels as the fused calls).  Layout and algorithm: DESIGN.md section 7.
+ *   qtable      per-row layer tables (+ optional scalar block: tr(K)/N and the shift values)
+ *   gram        one block of the Gram matrix (symmetric_lower: X1 == X2 rows, lower part + diagonal shift)
+ *   factor_diag Cholesky of a diagonal block, keeps inv(L) of every 128-block (linv_blocks [ceil(w/128)][128*128])
+ *   trsm        panel rows <- rows * L^-T by 128-block substitution
+ *   update      C -= A B^T with the (block-row-cyclic) lower mask: local row r of the region belongs to local
+ *               block r / cyc_db; its largest active column is r + base_shift + (r / cyc_db) (cyc_p - 1) cyc_db
+ *   sumsq, lml_finalize   reductions / closed form on (all-reduced) scalars */
+int smnngp_stage_qtable_f64(void* stream, const double* X, int64_t N, int64_t D, int n_hidden, int act, int arch,
+                            const double* hp_dev, double* tab, int64_t tab_ld, double* q, double* scal);
+int smnngp_stage_gram_f64(void* stream, const double* X1, int64_t n1, const double* X2, int64_t n2, int64_t D,
+                          int n_hidden, int act, int arch, const double* hp_dev, const double* tab1,
+                          int64_t tab_ld1, const double* tab2, int64_t tab_ld2, const double* scal, int shift,
+                          int symmetric_lower, double* K, int64_t ldk);
+int smnngp_stage_factor_diag_f64(void* stream, double* A, int64_t lda, int64_t w, double* linv_blocks,
+                                 double* logdet_dev, int* info_dev, int64_t gcol0);
+int smnngp_stage_trsm_f64(void* stream, double* R, int64_t ldr, int64_t m, int64_t w, const double* L, int64_t ldl,
+                          const double* linv_blocks);
+int smnngp_stage_update_f64(void* stream, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                            int64_t ldc, int64_t M, int64_t N, int64_t K, int lower, int64_t cyc_db, int64_t cyc_p,
+                            int64_t base_shift);
+int smnngp_stage_sumsq_f64(void* stream, const double* z, int64_t n, double* out_dev);
+int smnngp_stage_lml_finalize_f64(void* stream, const double* sums_dev, const double* hp_dev, int kind, int64_t N,
+                                  const int* info_dev, double* out_dev);
+
 /* ---- host-buffer entry points (what a ctypes / cgo / JNI caller without device arrays binds): inputs and
  * outputs are HOST pointers; device staging comes from a grow-only arena released by smnngp_host_release(). */
 int smnngp_lml_host_f64(const double* X, const double* y, int64_t N, int64_t D, int n_hidden, int act, int arch,

@@ -24,7 +24,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, double (&acc)
   const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
   // tile fully inside the matrix and (if masked) fully below the diagonal: batched 16-byte read-modify-write
   const bool interior = vec_ok && (r0 + tile_bm <= p.M) && (c0 + tile_bn <= p.N) &&
-                        (!p.lower || c0 + tile_bn - 1 <= r0);
+                        (c0 + tile_bn - 1 <= diag_limit(p, r0));
   if (interior) {
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -58,11 +58,12 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, double (&acc)
   for (int mi = 0; mi < MI; mi++) {
     const int r = rbase + mi * 8;
     if (r >= p.M) continue;
+    const long long lim = diag_limit(p, r);
 #pragma unroll
     for (int ni = 0; ni < NI; ni++) {
       const int c = cbase + ni * 8;
-      const bool ok0 = c < p.N && (!p.lower || c <= r);
-      const bool ok1 = (c + 1) < p.N && (!p.lower || (c + 1) <= r);
+      const bool ok0 = c < p.N && c <= lim;
+      const bool ok1 = (c + 1) < p.N && (c + 1) <= lim;
       double* dst = Cg + (long long)r * p.ldc + c;
       if (ok0 && ok1 && vec_ok) {
         double2* d2 = reinterpret_cast<double2*>(dst);
@@ -87,8 +88,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS) gemm_kernel(con
   extern __shared__ __align__(16) double smem[];
   const int ntn = (p.N + Cfg::BN - 1) / Cfg::BN;
   int ti, tj;
-  decode_tile<Cfg::Q>(blockIdx.x, ntn, p.lower, ti, tj);
+  decode_tile<Cfg::Q>(blockIdx.x, ntn, p.lower && p.cyc_db == 0, ti, tj);
   const int r0 = ti * Cfg::BM, c0 = tj * Cfg::BN;
+  if (p.cyc_db != 0 && c0 > diag_limit(p, min(r0 + Cfg::BM, p.M) - 1)) return;   // tile above the diagonal
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rbase = r0 + (warp / Cfg::WARPS_N) * 64 + (lane >> 2);
   const int cbase = c0 + (warp % Cfg::WARPS_N) * 32 + (lane & 3) * 2;
@@ -120,7 +122,8 @@ cudaError_t launch_gemm_sub_tma(cudaStream_t s, const GemmParams& p) {
   CUtensorMap ma, mb;
   if (!make_tmap(&ma, p.A, p.M, p.K, p.lda, TM_BM) || !make_tmap(&mb, p.B, p.N, p.K, p.ldb, TM_BN))
     return cudaErrorInvalidValue;
-  TmaShape sh{p.M, p.N, p.K, p.lower, count_tiles<TileTma>(p.M, p.N, p.lower)};
+  const int tri = p.lower && p.cyc_db == 0;
+  TmaShape sh{p.M, p.N, p.K, tri, count_tiles<TileTma>(p.M, p.N, tri), p.lower ? p.cyc_db : 0, p.cyc_p, p.base_shift};
   cudaError_t e = launch_tma_gemm<EpiSubTma>(s, ma, mb, sh, p, device_sm_count());
   instr().launches++;
   return e;
@@ -128,7 +131,7 @@ cudaError_t launch_gemm_sub_tma(cudaStream_t s, const GemmParams& p) {
 
 template <typename Cfg, int EPI>
 cudaError_t launch_gemm_cfg(cudaStream_t s, const GemmParams& p) {
-  long long tiles = count_tiles<Cfg>(p.M, p.N, p.lower);
+  long long tiles = count_tiles<Cfg>(p.M, p.N, p.lower && p.cyc_db == 0);
   bool a16 = (p.lda % 2 == 0) && (p.ldb % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
   auto kern = a16 ? gemm_kernel<Cfg, true, EPI> : gemm_kernel<Cfg, false, EPI>;
@@ -403,7 +406,7 @@ cudaError_t launch_potf2_trtri(cudaStream_t s, double* A, long long lda, int w, 
 }
 
 cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long Mtot, long long N, int NB,
-                            double* Linv_ws, double* logdet, int* info) {
+                            double* Linv_base, double* logdet, int* info, long long linv_stride) {
   if (NB < PB) NB = PB;
   NB = (NB / PB) * PB;
   cudaError_t e;
@@ -412,6 +415,7 @@ cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long 
     for (long long j0 = c0; j0 < c1; j0 += PB) {
       const long long j1 = (j0 + PB < N) ? j0 + PB : N;
       const int w = (int)(j1 - j0);
+      double* Linv_ws = Linv_base + (j0 / PB) * linv_stride;
       e = launch_potf2_trtri(s, A + j0 * lda + j0, lda, w, Linv_ws, logdet, info, (int)j0);
       if (e != cudaSuccess) return e;
       if (Mtot > j1) {

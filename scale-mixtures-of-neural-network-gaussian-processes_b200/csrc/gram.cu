@@ -206,7 +206,7 @@ cudaError_t launch_gram_tma(cudaStream_t s, const GramParams& p) {
   CUtensorMap ma, mb;
   if (!make_tmap(&ma, p.X1, p.N, p.D, p.ld1, TM_BM) || !make_tmap(&mb, p.X2, p.M, p.D, p.ld2, TM_BN))
     return cudaErrorInvalidValue;
-  TmaShape sh{p.N, p.M, p.D, p.symmetric, count_tiles<TileTma>(p.N, p.M, p.symmetric)};
+  TmaShape sh{p.N, p.M, p.D, p.symmetric, count_tiles<TileTma>(p.N, p.M, p.symmetric), 0, 1, 0};
   cudaError_t e = p.act == ACT_RELU ? launch_tma_gemm<EpiGramTma<ACT_RELU>>(s, ma, mb, sh, p, device_sm_count())
                                     : launch_tma_gemm<EpiGramTma<ACT_ERF>>(s, ma, mb, sh, p, device_sm_count());
   instr().launches++;

@@ -37,8 +37,18 @@ struct GemmParams {
   double* C;          // [M, N]
   long long lda, ldb, ldc;
   int M, N, K;
-  int lower;          // 1: C(0,0) is on the diagonal; only elements col <= row are touched
+  int lower;          // 1: only elements col <= diag_limit(row) are touched (C(0,0) on the diagonal by default)
+  // block-row-cyclic generalisation (multi-GPU local update): local row r lives in local block r / cyc_db whose
+  // global rows are shifted by (cyc_p - 1) * cyc_db per block; cyc_db == 0 -> plain lower triangle
+  int cyc_db, cyc_p, base_shift;
 };
+
+// largest active column of local row r (rows are non-decreasing in this limit)
+__host__ __device__ __forceinline__ long long diag_limit(const GemmParams& p, int r) {
+  if (!p.lower) return (1ll << 40);
+  if (p.cyc_db == 0) return r;
+  return (long long)r + p.base_shift + (long long)(r / p.cyc_db) * (p.cyc_p - 1) * p.cyc_db;
+}
 
 // ---- NNGP Gram -------------------------------------------------------------------------------------------
 // per-row layer table + final marginal variance (nngp diag) for X [N, D]
@@ -58,8 +68,9 @@ cudaError_t launch_gemm_store(cudaStream_t s, const GemmParams& p);
 cudaError_t launch_gemm_sub(cudaStream_t s, const GemmParams& p);
 // Blocked right-looking Cholesky of the leading N x N of the row-major trapezoid A [Mtot, N] (lower part);
 // rows N..Mtot-1 are carried along and end up as (rows) * L^-T.  NB = outer panel (multiple of 128).
+// linv_stride = 0: Linv_ws (128x128) is reused by every inner step; otherwise step k writes Linv_ws + k*linv_stride
 cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long Mtot, long long N, int NB,
-                            double* Linv_ws, double* logdet, int* info);
+                            double* Linv_ws, double* logdet, int* info, long long linv_stride = 0);
 
 // ---- reductions / closed forms ---------------------------------------------------------------------------
 cudaError_t launch_sumsq(cudaStream_t s, const double* z, long long n, double* out);

@@ -7,7 +7,7 @@
 //   thread).  Each group owns its own 128 x 64 output tile, its own 4-stage shared-memory ring and its own
 //   full / empty mbarriers, so the groups drift apart in time: while one group is in its epilogue (Gram
 //   recursion or the read-modify-write of the Cholesky update) or waits for the first slab of its next tile,
-//   the other group keeps the FP64 pipe busy (ping-pong).  Lanes 0 / 1 of the producer warp feed group 0 / 1:
+//   the other group keeps the FP64 pipe busy (ping-pong).  Lane 0 of producer warp g feeds group g:
 //   wait on the empty barrier, arm the full barrier with the slab's byte count, issue two cp.async.bulk.tensor
 //   (UTMALDG) loads - A box 16 x 128, B box 16 x 64, 128-byte swizzle, out-of-range rows / k zero-filled by
 //   the TMA unit.  The producer runs ahead across tile boundaries, so the ring is already full when a group
@@ -34,9 +34,18 @@ using TileTma = TileCfg<TM_BM, TM_BN, TM_STAGES, 1>;       // for count_tiles / 
 
 struct TmaShape {
   int M, N, K;          // output rows, cols, contraction length
-  int lower;            // tile list: 1 = only tiles touching col <= row
+  int lower;            // tile list: 1 = triangular enumeration (only tiles touching col <= row)
   long long tiles;
+  // block-row-cyclic mask (multi-GPU local update, see GemmParams): rectangular enumeration, inactive tiles skipped
+  int cyc_db, cyc_p, base_shift;
 };
+
+__device__ __forceinline__ bool tma_tile_active(const TmaShape& sh, int r0, int c0) {
+  if (sh.cyc_db == 0) return true;
+  const int rl = min(r0 + TM_BM, sh.M) - 1;
+  const long long lim = (long long)rl + sh.base_shift + (long long)(rl / sh.cyc_db) * (sh.cyc_p - 1) * sh.cyc_db;
+  return c0 <= lim;
+}
 
 // ---- host: tensor map for a row-major [rows, inner] FP64 operand (row pitch ld doubles) ---------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -137,10 +146,10 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const long long stride = 2ll * gridDim.x;
 
   if (warp < 4) {
-    // ===== producer warpgroup: lane g of warp 0 feeds group g =====
+    // ===== producer warpgroup: lane 0 of warp g feeds group g =====
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0 && lane < 2) {
-      const int g = lane;
+    if (warp < 2 && lane == 0) {
+      const int g = warp;
       const uint32_t gring = ring + g * TM_STAGES * TM_STAGE_BYTES;
       const uint32_t full0 = bars + 8 * (g * TM_STAGES), empty0 = bars + 8 * (2 * TM_STAGES + g * TM_STAGES);
       int s = 0;
@@ -149,6 +158,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         int ti, tj;
         decode_tile<2>(t, ntn, sh.lower, ti, tj);
         const int r0 = ti * TM_BM, c0 = tj * TM_BN;
+        if (!tma_tile_active(sh, r0, c0)) continue;
         for (int kt = 0; kt < KT; kt++) {
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           mbar_arrive_expect_tx(full0 + 8 * s, TM_STAGE_BYTES);
@@ -171,11 +181,12 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t off0 = (uint32_t)((((4 * (j & 1)) ^ g8) << 4) | ((j >> 1) << 3));
   const uint32_t a_off = (uint32_t)((wm * 64 + g8) * 128) + off0;
   const uint32_t b_off = (uint32_t)(TM_A_BYTES + (wn * 32 + g8) * 128) + off0;
-  int s = 0;
+  int s = 0, prev_stage = -1;
   uint32_t ph = 0;
   for (long long t = 2ll * blockIdx.x + g; t < sh.tiles; t += stride) {
     int ti, tj;
     decode_tile<2>(t, ntn, sh.lower, ti, tj);
+    if (!tma_tile_active(sh, ti * TM_BM, tj * TM_BN)) continue;
     double acc[MI][NI][2];
 #pragma unroll
     for (int mi = 0; mi < MI; mi++)
@@ -205,10 +216,19 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
           for (int ni = 0; ni < NI; ni++) dmma8x8x4(acc[mi][ni], a[cur][mi], b[cur][ni]);
       }
+      // Stage release is DELAYED BY ONE SLAB: ptxas is free to issue the mbarrier arrive right after the last
+      // ld.shared of a slab (before the DMMAs that consume the fragments), and a stage released while loads
+      // are still in flight was observed to be overwritten by the producer's next TMA (wrong fragments in ~0.3 %
+      // of the tiles).  Releasing slab k's stage at the end of slab k+1 puts a full slab of in-order DMMA issue
+      // - which cannot start before slab k's fragments have landed in registers - between load and release.
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty0 + 8 * s);
+      if (lane == 0 && prev_stage >= 0) mbar_arrive(empty0 + 8 * prev_stage);
+      prev_stage = s;
       if (++s == TM_STAGES) { s = 0; ph ^= 1u; }
     }
+    __syncwarp();
+    if (lane == 0 && prev_stage >= 0) mbar_arrive(empty0 + 8 * prev_stage);
+    prev_stage = -1;
     Epi::apply(ep, acc, ti * TM_BM, tj * TM_BN, wm, wn, lane);
   }
 }

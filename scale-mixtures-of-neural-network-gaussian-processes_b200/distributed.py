@@ -1,0 +1,250 @@
+"""Multi-GPU exact-GP log marginal likelihood: one process per GPU (torch.distributed, NCCL over NVLink),
+block-row-cyclic layout, right-looking blocked Cholesky with the solves fused in.
+
+Layout (P ranks, distribution block DB = outer panel width, rows 0..N-1 = K + eps I, row N = y^T):
+  global block b = rows [b DB, (b+1) DB) lives on rank b mod P, full width, lower part only.  Every rank holds
+  all of X (376 MB at C3) and generates exactly the Gram rows it owns - the N x N matrix never exists in one
+  place and there is no exchange step in the Gram stage.
+Per panel p (columns [c0, c1)):
+  owner factors the DB x DB diagonal block           -> ONE broadcast of (L_pp, block inverses)  [2.6 MB]
+  every rank TRSMs its own panel rows (tensor pipe)  -> ONE all-gather of the panel             [<= 245 MB]
+  every rank updates its own trailing rows with a single kernel launch (block-row-cyclic lower mask).
+This is the P x 1 case of a 2-D block-cyclic grid.  With NVSwitch every rank receives the whole panel at full
+link bandwidth (14.4 GB per rank over the whole factorisation at C3, ~20 ms at 700 GB/s vs ~300 ms of math), so a
+second grid dimension would only shrink a term that is already negligible, while P x 1 spreads the TRSM over all
+ranks and needs two collectives per panel instead of four.
+
+The orchestration below is backend-agnostic: ``CudaBackend`` drives the stage-level C-ABI (product path);
+the CPU test-suite injects a NumPy backend to exercise the ownership / exchange logic under gloo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .device import ACT, ARCH, KIND, SHIFT, StackSpec
+
+PB = 128
+
+
+def _cdiv(a, b):
+    return (a + b - 1) // b
+
+
+class BlockRowCyclic:
+    """Pure host logic: which global rows live where."""
+
+    def __init__(self, m_total: int, n_cols: int, world: int, rank: int, db: int):
+        assert db % PB == 0
+        self.m_total, self.n, self.P, self.rank, self.db = m_total, n_cols, world, rank, db
+        self.nblocks = _cdiv(m_total, db)
+
+    def owner(self, b):
+        return b % self.P
+
+    def block_rows(self, b):
+        return min((b + 1) * self.db, self.m_total) - b * self.db
+
+    def local_blocks(self, rank=None):
+        r = self.rank if rank is None else rank
+        return list(range(r, self.nblocks, self.P))
+
+    def local_rows(self, rank=None):
+        return sum(self.block_rows(b) for b in self.local_blocks(rank))
+
+    def local_offset(self, b, rank=None):
+        """local row offset of global block b on its owner"""
+        r = self.owner(b) if rank is None else rank
+        return sum(self.block_rows(x) for x in range(r, b, self.P))
+
+    def first_block_from(self, gb, rank=None):
+        """smallest block index >= gb owned by rank (may be >= nblocks)"""
+        r = self.rank if rank is None else rank
+        return gb + ((r - gb) % self.P)
+
+    def rows_from_block(self, gb, rank=None):
+        """(local row offset, row count) of this rank's rows in global blocks >= gb"""
+        r = self.rank if rank is None else rank
+        fb = self.first_block_from(gb, r)
+        if fb >= self.nblocks:
+            return self.local_rows(r), 0
+        off = self.local_offset(fb, r)
+        return off, self.local_rows(r) - off
+
+
+class CudaBackend:
+    """Stage-level C-ABI on torch CUDA tensors (views keep their row pitch)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.lib = _lib.load()
+
+    def _s(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr())
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"libsmnngp stage '{what}' failed with status {rc}")
+
+    def empty(self, *shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def zeros(self, *shape, dtype=torch.float64):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def qtable(self, x, spec: StackSpec, hp):
+        nh, act, arch = spec.ids()
+        n, d = x.shape
+        n_act = max(nh + (1 if arch == 1 else 0), 1)
+        tab, q, scal = self.empty(n_act, n), self.empty(n), self.zeros(16)
+        self._ck(self.lib.smnngp_stage_qtable_f64(self._s(), self._p(x), n, d, nh, act, arch, self._p(hp), self._p(tab),
+                                                  n, self._p(q), self._p(scal)), "qtable")
+        return tab, q, scal
+
+    def gram_block(self, x1, x2, spec, hp, tab1, tab2, scal, shift, symmetric_lower, out):
+        nh, act, arch = spec.ids()
+        self._ck(self.lib.smnngp_stage_gram_f64(self._s(), self._p(x1), x1.shape[0], self._p(x2), x2.shape[0],
+                                                x1.shape[1], nh, act, arch, self._p(hp), self._p(tab1), tab1.stride(0),
+                                                self._p(tab2), tab2.stride(0), self._p(scal), SHIFT[shift],
+                                                1 if symmetric_lower else 0, self._p(out), out.stride(0)), "gram")
+
+    def factor_diag(self, a, linv, logdet, info, gcol0):
+        self._ck(self.lib.smnngp_stage_factor_diag_f64(self._s(), self._p(a), a.stride(0), a.shape[0], self._p(linv),
+                                                       self._p(logdet), self._p(info), gcol0), "factor_diag")
+
+    def trsm(self, r, ldiag, linv):
+        self._ck(self.lib.smnngp_stage_trsm_f64(self._s(), self._p(r), r.stride(0), r.shape[0], r.shape[1],
+                                                self._p(ldiag), ldiag.stride(0), self._p(linv)), "trsm")
+
+    def update(self, a, b, c, lower, cyc_db, cyc_p, base_shift):
+        self._ck(self.lib.smnngp_stage_update_f64(self._s(), self._p(a), a.stride(0), self._p(b), b.stride(0),
+                                                  self._p(c), c.stride(0), c.shape[0], c.shape[1], a.shape[1],
+                                                  1 if lower else 0, cyc_db, cyc_p, base_shift), "update")
+
+    def sumsq(self, z, out):
+        self._ck(self.lib.smnngp_stage_sumsq_f64(self._s(), self._p(z), z.shape[0], self._p(out)), "sumsq")
+
+    def lml_finalize(self, sums, hp, kind, n, info):
+        out = self.empty(4)
+        self._ck(self.lib.smnngp_stage_lml_finalize_f64(self._s(), self._p(sums), self._p(hp), KIND[kind], n,
+                                                        self._p(info), self._p(out)), "lml_finalize")
+        return out
+
+
+def default_block(n, world):
+    """distribution block = outer panel width: wide enough for the update kernel, small enough to balance"""
+    per_rank = n / max(world, 1)
+    if per_rank >= 4096:
+        return 512
+    if per_rank >= 1024:
+        return 256
+    return 128
+
+
+class DistributedLML:
+    """SPR.loss (spax/models.py:93-98) sharded over the ranks of a process group.  Strong scaling: the problem
+    is fixed, every rank owns ~1/P of the rows."""
+
+    def __init__(self, n, d, spec: StackSpec, device, group=None, block=None, backend=None):
+        self.n, self.d, self.spec = int(n), int(d), spec
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.db = int(block) if block else default_block(self.n, self.world)
+        self.be = backend if backend is not None else CudaBackend(device)
+        self.lay = BlockRowCyclic(self.n + 1, self.n, self.world, self.rank, self.db)
+        self.ld = _cdiv(self.n, 16) * 16
+        self.mloc = self.lay.local_rows()
+        self.a = self.be.empty(max(self.mloc, 1), self.ld)
+        nblk = self.db // PB
+        self.diag = self.be.empty(self.db * self.db + nblk * PB * PB)
+        # largest per-rank panel piece over all panels (panel p -> rows in blocks >= p + 1)
+        self.max_m = max(self.lay.rows_from_block(1, r)[1] for r in range(self.world)) if self.world > 1 else 0
+        self.send = self.be.empty(max(self.max_m, 1), self.db) if self.world > 1 else None
+        self.gath = self.be.empty(self.world * max(self.max_m, 1), self.db) if self.world > 1 else None
+
+    # ---- stages ----------------------------------------------------------------------------------------------
+    def _build_gram(self, x, y, hp):
+        be, lay, n, db = self.be, self.lay, self.n, self.db
+        tab, q, scal = be.qtable(x, self.spec, hp)
+        for b in lay.local_blocks():
+            g0 = b * db
+            lo = lay.local_offset(b)
+            rows = min(g0 + lay.block_rows(b), n) - g0                 # rows of the square part in this block
+            if rows > 0:
+                xb = x[g0:g0 + rows]
+                if g0 > 0:                                               # rectangle left of the diagonal block
+                    be.gram_block(xb, x[:g0], self.spec, hp, tab[:, g0:], tab, scal, "none", False,
+                                  self.a[lo:lo + rows, :g0])
+                be.gram_block(xb, xb, self.spec, hp, tab[:, g0:], tab[:, g0:], scal, "eps_abs", True,
+                              self.a[lo:lo + rows, g0:g0 + rows])       # K + eps I (spax/models.py:96)
+            if g0 <= n < g0 + lay.block_rows(b):                         # the appended row y^T
+                self.a[lo + (n - g0), :n].copy_(y)
+
+    def _gather_index(self, p, c1):
+        """position of global rows [c1, N) inside the padded all-gather buffer (rank-major)"""
+        lay, db, P = self.lay, self.db, self.world
+        gr = torch.arange(c1, self.n, device=self.a.device, dtype=torch.int64)
+        gb = gr // db
+        r = gb % P
+        fb = (p + 1) + ((r - (p + 1)) % P)
+        return r * max(self.max_m, 1) + ((gb - fb) // P) * db + gr % db
+
+    def lml(self, x, y, hp, kind="student_t"):
+        be, lay, n, db, P = self.be, self.lay, self.n, self.db, self.world
+        self._build_gram(x, y, hp)
+        sums = be.zeros(2)
+        info = be.zeros(1, dtype=torch.int32)
+        nblk = db // PB
+        for p in range(_cdiv(n, db)):
+            c0, c1 = p * db, min((p + 1) * db, n)
+            w = c1 - c0
+            owner = lay.owner(p)
+            ldiag = self.diag[:w * w].view(w, w)
+            linv = self.diag[db * db:db * db + nblk * PB * PB]
+            if self.rank == owner:
+                lo = lay.local_offset(p)
+                blk = self.a[lo:lo + w, c0:c1]
+                be.factor_diag(blk, linv, sums[0:1], info, c0)
+                ldiag.copy_(blk)
+            if P > 1:
+                dist.broadcast(self.diag, src=dist.get_global_rank(self.group, owner) if self.group else owner,
+                               group=self.group)
+            # this rank's rows with global index >= c1: on the owner whatever follows the diagonal rows (the rest of
+            # block p, i.e. the appended row when the block straddles N, then its later blocks), elsewhere all
+            # local blocks >= p + 1.  Both are suffixes of the local storage.
+            if self.rank == owner:
+                ls = lay.local_offset(p) + w
+                m = self.mloc - ls
+            else:
+                ls, m = lay.rows_from_block(p + 1)
+            if m > 0:
+                be.trsm(self.a[ls:ls + m, c0:c1], ldiag, linv)
+            if c1 >= n:
+                continue
+            if P > 1:
+                if m > 0:
+                    self.send[:m, :w].copy_(self.a[ls:ls + m, c0:c1])
+                dist.all_gather_into_tensor(self.gath, self.send, group=self.group)
+                pfull = self.gath[:, :w].index_select(0, self._gather_index(p, c1))
+            else:
+                pfull = self.a[ls:ls + (n - c1), c0:c1]
+            if m > 0:
+                gb0 = lay.first_block_from(p + 1)
+                be.update(self.a[ls:ls + m, c0:c1], pfull, self.a[ls:ls + m, c1:n], True, db, P, gb0 * db - c1)
+        # z = (L^-1 y)^T sits in global row N on its owner
+        bn = n // db
+        if self.rank == lay.owner(bn):
+            lrow = lay.local_offset(bn) + (n - bn * db)
+            be.sumsq(self.a[lrow, :n], sums[1:2])
+        if P > 1:
+            dist.all_reduce(sums, group=self.group)
+            dist.all_reduce(info, op=dist.ReduceOp.MAX, group=self.group)
+        return be.lml_finalize(sums, hp, kind, n, info), info

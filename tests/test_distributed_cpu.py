@@ -1,0 +1,75 @@
+"""world_size-2 (and 3) gloo runs of the multi-GPU driver's host logic on CPU, NumPy backend as the arithmetic."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n, d, db, kind, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import smnngp_b200 as sm
+        from smnngp_b200.distributed import DistributedLML
+        from tests.np_backend import NumpyBackend
+        from tests.synth import regression_data, DEFAULT_HP as hp
+        x, y, *_ = regression_data(n, d)
+        spec = sm.StackSpec(3, "relu", "mlp")
+        hpt = torch.tensor([hp[k] for k in ("w_std", "b_std", "last_w_std", "eps", "alpha", "beta")], dtype=torch.float64)
+        solver = DistributedLML(n, d, spec, "cpu", block=db, backend=NumpyBackend())
+        out, info = solver.lml(torch.from_numpy(x), torch.from_numpy(y), hpt, kind=kind)
+        q.put((rank, out.tolist(), int(info[0])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,db,kind", [(2, 700, 128, "student_t"), (2, 512, 256, "gauss"), (3, 900, 128, "student_t"),
+                                             (2, 130, 128, "student_t")])
+def test_block_row_cyclic_lml_matches_oracle(world, n, db, kind):
+    from oracle import nngp_oracle as orc
+    from tests.synth import regression_data, DEFAULT_HP as hp
+    d = 6
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + n) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, d, db, kind, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, y, *_ = regression_data(n, d)
+    ref = orc.spr_loss(x, y, num_hiddens=3, act="relu", arch="mlp", w_std=hp["w_std"], b_std=hp["b_std"],
+                       last_w_std=hp["last_w_std"], eps=hp["eps"], kind=kind, a=hp["alpha"], b=hp["beta"])
+    for rank, out, info in res:
+        assert info == 0
+        assert abs(out[1] - ref) <= 1e-9 * abs(ref), (rank, out[1], ref)
+    assert res[0][1] == res[1][1], "every rank must hold the same result"
+
+
+def test_layout_bookkeeping():
+    from smnngp_b200.distributed import BlockRowCyclic
+    for (m, P, db) in [(701, 2, 128), (1025, 3, 256), (60001, 8, 512), (513, 4, 128), (129, 2, 128)]:
+        seen = np.zeros(m, dtype=int)
+        for r in range(P):
+            lay = BlockRowCyclic(m, m - 1, P, r, db)
+            off = 0
+            for b in lay.local_blocks():
+                assert lay.owner(b) == r and lay.local_offset(b) == off
+                seen[b * db: b * db + lay.block_rows(b)] += 1
+                off += lay.block_rows(b)
+            assert off == lay.local_rows()
+            for gb in range(lay.nblocks + 1):
+                o, cnt = lay.rows_from_block(gb)
+                want = sum(lay.block_rows(b) for b in lay.local_blocks() if b >= gb)
+                assert cnt == want and o == lay.local_rows() - want
+        assert (seen == 1).all()

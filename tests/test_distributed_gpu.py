@@ -1,0 +1,78 @@
+"""Multi-GPU driver on real devices: P = 1 always; P = 2 (NCCL) when the box has two GPUs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ref(n, d, kind):
+    from oracle import nngp_oracle as orc
+    from tests.synth import regression_data, DEFAULT_HP as hp
+    x, y, *_ = regression_data(n, d)
+    return orc.spr_loss(x, y, num_hiddens=3, act="relu", arch="mlp", w_std=hp["w_std"], b_std=hp["b_std"],
+                        last_w_std=hp["last_w_std"], eps=hp["eps"], kind=kind, a=hp["alpha"], b=hp["beta"])
+
+
+@pytest.mark.parametrize("n,db", [(700, 128), (1024, 256), (2500, 512), (130, 128)])
+def test_single_rank_stage_path_matches_oracle_and_fused(n, db):
+    import torch
+    import smnngp_b200 as sm
+    from smnngp_b200.distributed import DistributedLML
+    from tests.synth import regression_data, DEFAULT_HP as hp
+    d = 8
+    x, y, *_ = regression_data(n, d)
+    spec = sm.StackSpec(3, "relu", "mlp")
+    hpd = sm.make_hp(**hp)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    solver = DistributedLML(n, d, spec, "cuda", block=db)
+    out, info = solver.lml(xd, yd, hpd, kind="student_t")
+    ref = _ref(n, d, "student_t")
+    assert int(info.item()) == 0
+    assert abs(out[1].item() - ref) <= 1e-8 * abs(ref)
+    fused, _ = sm.device.lml(xd, yd, spec=spec, hp=hpd)
+    assert abs(out[1].item() - fused[1].item()) <= 1e-12 * abs(ref)
+
+
+def _worker(rank, world, port, n, d, db, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import smnngp_b200 as sm
+        from smnngp_b200.distributed import DistributedLML
+        from tests.synth import regression_data, DEFAULT_HP as hp
+        x, y, *_ = regression_data(n, d)
+        dev = torch.device("cuda", rank)
+        solver = DistributedLML(n, d, sm.StackSpec(3, "relu", "mlp"), dev, block=db)
+        out, info = solver.lml(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), sm.make_hp(device=dev, **hp))
+        q.put((rank, out.cpu().tolist(), int(info.item())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,db", [(1500, 128), (3000, 256)])
+def test_two_rank_nccl_matches_oracle(n, db):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, 29700 + n % 100, n, 8, db, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = _ref(n, 8, "student_t")
+    for rank, out, info in res:
+        assert info == 0 and abs(out[1] - ref) <= 1e-8 * abs(ref)

@@ -277,3 +277,25 @@ def test_golden_vectors_on_gpu(sm):
             assert np.abs(mean.cpu().numpy() - g[f"mean{vi}"]).max() <= LML_TOL * np.abs(g[f"mean{vi}"]).max()
             assert np.abs(var.cpu().numpy() - g[f"var{vi}"]).max() <= LML_TOL * np.abs(g[f"var{vi}"]).max()
             assert abs(nll.item() - float(g[f"nll_{key}{vi}"])) <= LML_TOL * abs(float(g[f"nll_{key}{vi}"]))
+
+
+@pytest.mark.parametrize("m,n,k,lower", [(2745, 2744, 256, 1), (2816, 2752, 256, 0), (4096, 4160, 16, 0),
+                                         (4096, 4096, 128, 0), (8192, 8256, 512, 1), (1000, 130, 48, 0)])
+def test_update_kernel_many_tiles_per_cta(sm, m, n, k, lower):
+    """C -= A B^T on the TMA-fed persistent kernel when every math group walks through several tiles (regression
+    test for the stage-release race: a stage released while ld.shared was in flight got overwritten by TMA)."""
+    import torch
+    from smnngp_b200.distributed import CudaBackend
+    be = CudaBackend("cuda")
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, k, dtype=torch.float64, device="cuda")
+    c0 = torch.randn(m, n, dtype=torch.float64, device="cuda")
+    ref = c0 - a @ b.T
+    if lower:
+        mask = torch.arange(n, device="cuda")[None, :] <= torch.arange(m, device="cuda")[:, None]
+        ref = torch.where(mask, ref, c0)
+    for _ in range(4):
+        c = c0.clone()
+        be.update(a, b, c, bool(lower), 0, 1, 0)
+        assert float((c - ref).abs().max()) <= 1e-11 * k
