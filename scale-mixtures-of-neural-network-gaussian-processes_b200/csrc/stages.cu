@@ -88,7 +88,18 @@ int smnngp_stage_update_f64(void* stream, const double* A, int64_t lda, const do
   u.A = A; u.lda = lda; u.B = B; u.ldb = ldb; u.C = C; u.ldc = ldc;
   u.M = (int)M; u.N = (int)N; u.K = (int)K; u.lower = lower;
   u.cyc_db = (int)cyc_db; u.cyc_p = (int)cyc_p; u.base_shift = (int)base_shift;
-  return fail_stage(launch_gemm_sub(s, u));
+  const bool timed = instr().time_updates && K >= 256;      // outer trailing updates only
+  if (timed) {
+    double pairs = 0.0;                                      // active (row, col) pairs of this rank's part
+    for (int64_t r = 0; r < M; r++) {
+      long long lim = diag_limit(u, (int)r) + 1;
+      pairs += (double)(lim < N ? (lim > 0 ? lim : 0) : N);
+    }
+    instr_begin_update(s, 2.0 * pairs * (double)K);
+  }
+  cudaError_t e = launch_gemm_sub(s, u);
+  if (timed) instr_end_update(s);
+  return fail_stage(e);
 }
 
 int smnngp_stage_sumsq_f64(void* stream, const double* z, int64_t n, double* out_dev) {

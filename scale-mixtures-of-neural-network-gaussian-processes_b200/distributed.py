@@ -169,6 +169,9 @@ class DistributedLML:
         self.max_m = max(self.lay.rows_from_block(1, r)[1] for r in range(self.world)) if self.world > 1 else 0
         self.send = self.be.empty(max(self.max_m, 1), self.db) if self.world > 1 else None
         self.gath = self.be.empty(self.world * max(self.max_m, 1), self.db) if self.world > 1 else None
+        # panel in global row order, double buffered (look-ahead prepares panel p + 1 while panel p is in use)
+        self.pfull = [self.be.empty(self.n, self.db) for _ in range(2)] if self.world > 1 else None
+        self.side = torch.cuda.Stream(device=self.a.device) if self.a.is_cuda else None
 
     # ---- stages ----------------------------------------------------------------------------------------------
     def _build_gram(self, x, y, hp):
@@ -197,48 +200,97 @@ class DistributedLML:
         fb = (p + 1) + ((r - (p + 1)) % P)
         return r * max(self.max_m, 1) + ((gb - fb) // P) * db + gr % db
 
+    # ---- one panel: diagonal block, broadcast, TRSM of the local rows, all-gather of the panel ---------------
+    def _panel(self, p, sums, info, slot):
+        """Runs on the CURRENT stream.  Returns (ls, m, pfull): this rank's rows below the diagonal block and the
+        whole panel for global rows [c1, N) in global order (None for the last panel)."""
+        be, lay, n, db, P = self.be, self.lay, self.n, self.db, self.world
+        nblk = db // PB
+        c0, c1 = p * db, min((p + 1) * db, n)
+        w = c1 - c0
+        owner = lay.owner(p)
+        ldiag = self.diag[:w * w].view(w, w)
+        linv = self.diag[db * db:db * db + nblk * PB * PB]
+        if self.rank == owner:
+            lo = lay.local_offset(p)
+            blk = self.a[lo:lo + w, c0:c1]
+            be.factor_diag(blk, linv, sums[0:1], info, c0)
+            ldiag.copy_(blk)
+        if P > 1:
+            dist.broadcast(self.diag, src=dist.get_global_rank(self.group, owner) if self.group else owner,
+                           group=self.group)
+        # this rank's rows with global index >= c1: on the owner whatever follows the diagonal rows (the rest of
+        # block p, i.e. the appended row when the block straddles N, then its later blocks), elsewhere all
+        # local blocks >= p + 1.  Both are suffixes of the local storage.
+        if self.rank == owner:
+            ls = lay.local_offset(p) + w
+            m = self.mloc - ls
+        else:
+            ls, m = lay.rows_from_block(p + 1)
+        if m > 0:
+            be.trsm(self.a[ls:ls + m, c0:c1], ldiag, linv)
+        if c1 >= n:
+            return ls, m, None
+        if P > 1:
+            if m > 0:
+                self.send[:m, :w].copy_(self.a[ls:ls + m, c0:c1])
+            dist.all_gather_into_tensor(self.gath, self.send, group=self.group)
+            pfull = self.pfull[slot][:n - c1]
+            torch.index_select(self.gath, 0, self._gather_index(p, c1), out=pfull)
+        else:
+            pfull = self.a[ls:ls + (n - c1), c0:c1]
+        return ls, m, pfull
+
     def lml(self, x, y, hp, kind="student_t"):
+        """Right-looking factorisation with one panel of look-ahead: while the bulk of panel p's trailing update
+        runs on the main stream, the next panel (diagonal block, broadcast, TRSM, all-gather) is prepared on a
+        side stream as soon as its block column has been updated."""
         be, lay, n, db, P = self.be, self.lay, self.n, self.db, self.world
         self._build_gram(x, y, hp)
         sums = be.zeros(2)
         info = be.zeros(1, dtype=torch.int32)
-        nblk = db // PB
-        for p in range(_cdiv(n, db)):
+        npanels = _cdiv(n, db)
+        cuda = self.a.is_cuda
+        main = torch.cuda.current_stream(self.a.device) if cuda else None
+        side = self.side if cuda else None
+
+        def on_side():
+            return torch.cuda.stream(side) if cuda else _NullCtx()
+
+        if cuda:
+            side.wait_stream(main)
+        with on_side():
+            cur = self._panel(0, sums, info, 0)
+        if cuda:
+            ev_panel = torch.cuda.Event()
+            ev_panel.record(side)
+        for p in range(npanels):
             c0, c1 = p * db, min((p + 1) * db, n)
-            w = c1 - c0
-            owner = lay.owner(p)
-            ldiag = self.diag[:w * w].view(w, w)
-            linv = self.diag[db * db:db * db + nblk * PB * PB]
-            if self.rank == owner:
-                lo = lay.local_offset(p)
-                blk = self.a[lo:lo + w, c0:c1]
-                be.factor_diag(blk, linv, sums[0:1], info, c0)
-                ldiag.copy_(blk)
-            if P > 1:
-                dist.broadcast(self.diag, src=dist.get_global_rank(self.group, owner) if self.group else owner,
-                               group=self.group)
-            # this rank's rows with global index >= c1: on the owner whatever follows the diagonal rows (the rest of
-            # block p, i.e. the appended row when the block straddles N, then its later blocks), elsewhere all
-            # local blocks >= p + 1.  Both are suffixes of the local storage.
-            if self.rank == owner:
-                ls = lay.local_offset(p) + w
-                m = self.mloc - ls
-            else:
-                ls, m = lay.rows_from_block(p + 1)
-            if m > 0:
-                be.trsm(self.a[ls:ls + m, c0:c1], ldiag, linv)
+            ls, m, pfull = cur
+            if cuda:
+                main.wait_event(ev_panel)                                  # panel p is factored and gathered
             if c1 >= n:
-                continue
-            if P > 1:
-                if m > 0:
-                    self.send[:m, :w].copy_(self.a[ls:ls + m, c0:c1])
-                dist.all_gather_into_tensor(self.gath, self.send, group=self.group)
-                pfull = self.gath[:, :w].index_select(0, self._gather_index(p, c1))
-            else:
-                pfull = self.a[ls:ls + (n - c1), c0:c1]
+                break
+            gb0 = lay.first_block_from(p + 1)
+            shift = gb0 * db - c1
+            na = min(db, n - c1)                                           # next panel's block column first
             if m > 0:
-                gb0 = lay.first_block_from(p + 1)
-                be.update(self.a[ls:ls + m, c0:c1], pfull, self.a[ls:ls + m, c1:n], True, db, P, gb0 * db - c1)
+                be.update(self.a[ls:ls + m, c0:c1], pfull[:na], self.a[ls:ls + m, c1:c1 + na], True, db, P, shift)
+            if cuda:
+                ev_a = torch.cuda.Event()
+                ev_a.record(main)
+                side.wait_event(ev_a)
+            with on_side():                                                # look-ahead: prepare panel p + 1
+                nxt = self._panel(p + 1, sums, info, (p + 1) & 1)
+            if cuda:
+                ev_panel = torch.cuda.Event()
+                ev_panel.record(side)
+            if m > 0 and c1 + na < n:                                      # the rest of the trailing matrix
+                be.update(self.a[ls:ls + m, c0:c1], pfull[na:], self.a[ls:ls + m, c1 + na:n], True, db, P,
+                          shift - na)
+            cur = nxt
+        if cuda:
+            main.wait_stream(side)
         # z = (L^-1 y)^T sits in global row N on its owner
         bn = n // db
         if self.rank == lay.owner(bn):
@@ -248,3 +300,11 @@ class DistributedLML:
             dist.all_reduce(sums, group=self.group)
             dist.all_reduce(info, op=dist.ReduceOp.MAX, group=self.group)
         return be.lml_finalize(sums, hp, kind, n, info), info
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
