@@ -110,7 +110,8 @@ int smnngp_test_nll_f64(void* stream, const double* X, const double* y, const do
  *   factor_diag Cholesky of a diagonal block, keeps inv(L) of every 128-block (linv_blocks [ceil(w/128)][128*128])
  *   trsm        panel rows <- rows * L^-T by 128-block substitution
  *   update      C -= A B^T with the (block-row-cyclic) lower mask: local row r of the region belongs to local
- *               block r / cyc_db; its largest active column is r + base_shift + (r / cyc_db) (cyc_p - 1) cyc_db
+ *               block r / cyc_db; its largest active column is r + base_shift + (r / cyc_db) (cyc_p - 1) cyc_db;
+ *               sm_reserve SMs are left free for look-ahead work running on another stream
  *   sumsq, lml_finalize   reductions / closed form on (all-reduced) scalars */
 int smnngp_stage_qtable_f64(void* stream, const double* X, int64_t N, int64_t D, int n_hidden, int act, int arch,
                             const double* hp_dev, double* tab, int64_t tab_ld, double* q, double* scal);
@@ -124,7 +125,7 @@ int smnngp_stage_trsm_f64(void* stream, double* R, int64_t ldr, int64_t m, int64
                           const double* linv_blocks);
 int smnngp_stage_update_f64(void* stream, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                             int64_t ldc, int64_t M, int64_t N, int64_t K, int lower, int64_t cyc_db, int64_t cyc_p,
-                            int64_t base_shift);
+                            int64_t base_shift, int sm_reserve);
 int smnngp_stage_sumsq_f64(void* stream, const double* z, int64_t n, double* out_dev);
 int smnngp_stage_lml_finalize_f64(void* stream, const double* sums_dev, const double* hp_dev, int kind, int64_t N,
                                   const int* info_dev, double* out_dev);

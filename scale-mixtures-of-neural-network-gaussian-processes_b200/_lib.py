@@ -120,7 +120,7 @@ def _declare(lib):
     lib.smnngp_stage_factor_diag_f64.argtypes = [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64]
     lib.smnngp_stage_trsm_f64.argtypes = [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]
     lib.smnngp_stage_update_f64.argtypes = [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i, _i64, _i64,
-                                            _i64]
+                                            _i64, _i]
     lib.smnngp_stage_sumsq_f64.argtypes = [_vp, _vp, _i64, _vp]
     lib.smnngp_stage_lml_finalize_f64.argtypes = [_vp, _vp, _vp, _i, _i64, _vp, _vp]
     lib.smnngp_instr_reset.restype = None

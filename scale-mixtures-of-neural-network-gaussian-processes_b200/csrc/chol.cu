@@ -124,7 +124,9 @@ cudaError_t launch_gemm_sub_tma(cudaStream_t s, const GemmParams& p) {
     return cudaErrorInvalidValue;
   const int tri = p.lower && p.cyc_db == 0;
   TmaShape sh{p.M, p.N, p.K, tri, count_tiles<TileTma>(p.M, p.N, tri), p.lower ? p.cyc_db : 0, p.cyc_p, p.base_shift};
-  cudaError_t e = launch_tma_gemm<EpiSubTma>(s, ma, mb, sh, p, device_sm_count());
+  int sms = device_sm_count() - p.sm_reserve;
+  if (sms < 8) sms = 8;
+  cudaError_t e = launch_tma_gemm<EpiSubTma>(s, ma, mb, sh, p, sms);
   instr().launches++;
   return e;
 }

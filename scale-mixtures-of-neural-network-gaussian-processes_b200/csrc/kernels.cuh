@@ -41,6 +41,7 @@ struct GemmParams {
   // block-row-cyclic generalisation (multi-GPU local update): local row r lives in local block r / cyc_db whose
   // global rows are shifted by (cyc_p - 1) * cyc_db per block; cyc_db == 0 -> plain lower triangle
   int cyc_db, cyc_p, base_shift;
+  int sm_reserve;     // persistent kernel leaves this many SMs free (look-ahead work on another stream)
 };
 
 // largest active column of local row r (rows are non-decreasing in this limit)

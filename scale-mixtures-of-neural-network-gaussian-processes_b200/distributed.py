@@ -20,6 +20,7 @@ the CPU test-suite injects a NumPy backend to exercise the ownership / exchange 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -123,10 +124,11 @@ class CudaBackend:
         self._ck(self.lib.smnngp_stage_trsm_f64(self._s(), self._p(r), r.stride(0), r.shape[0], r.shape[1],
                                                 self._p(ldiag), ldiag.stride(0), self._p(linv)), "trsm")
 
-    def update(self, a, b, c, lower, cyc_db, cyc_p, base_shift):
+    def update(self, a, b, c, lower, cyc_db, cyc_p, base_shift, sm_reserve=0):
         self._ck(self.lib.smnngp_stage_update_f64(self._s(), self._p(a), a.stride(0), self._p(b), b.stride(0),
                                                   self._p(c), c.stride(0), c.shape[0], c.shape[1], a.shape[1],
-                                                  1 if lower else 0, cyc_db, cyc_p, base_shift), "update")
+                                                  1 if lower else 0, cyc_db, cyc_p, base_shift, int(sm_reserve)),
+                 "update")
 
     def sumsq(self, z, out):
         self._ck(self.lib.smnngp_stage_sumsq_f64(self._s(), self._p(z), z.shape[0], self._p(out)), "sumsq")
@@ -171,7 +173,10 @@ class DistributedLML:
         self.gath = self.be.empty(self.world * max(self.max_m, 1), self.db) if self.world > 1 else None
         # panel in global row order, double buffered (look-ahead prepares panel p + 1 while panel p is in use)
         self.pfull = [self.be.empty(self.n, self.db) for _ in range(2)] if self.world > 1 else None
-        self.side = torch.cuda.Stream(device=self.a.device) if self.a.is_cuda else None
+        self.side = torch.cuda.Stream(device=self.a.device, priority=-1) if self.a.is_cuda else None
+        # SMs the bulk update leaves free so the look-ahead chain (diagonal block, TRSM, NCCL) really overlaps:
+        # the persistent update kernel otherwise occupies every SM until it ends
+        self.sm_reserve = int(os.environ.get("SMNNGP_SM_RESERVE", "8" if self.world > 1 else "0"))
 
     # ---- stages ----------------------------------------------------------------------------------------------
     def _build_gram(self, x, y, hp):
@@ -287,7 +292,7 @@ class DistributedLML:
                 ev_panel.record(side)
             if m > 0 and c1 + na < n:                                      # the rest of the trailing matrix
                 be.update(self.a[ls:ls + m, c0:c1], pfull[na:], self.a[ls:ls + m, c1 + na:n], True, db, P,
-                          shift - na)
+                          shift - na, self.sm_reserve)
             cur = nxt
         if cuda:
             main.wait_stream(side)

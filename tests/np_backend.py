@@ -52,7 +52,7 @@ class NumpyBackend:
         rn, L = r.numpy(), np.tril(ldiag.numpy())
         rn[...] = sla.solve_triangular(L, rn.T, lower=True).T
 
-    def update(self, a, b, c, lower, cyc_db, cyc_p, base_shift):
+    def update(self, a, b, c, lower, cyc_db, cyc_p, base_shift, sm_reserve=0):
         an, bn, cn = a.numpy(), b.numpy(), c.numpy()
         full = an @ bn.T
         rows = np.arange(cn.shape[0])
