@@ -262,10 +262,14 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (Cholesky trailing update, FP64 tensor pipe) ----
     peak = float(lib.smnngp_dmma_peak_tflops())
     achieved = (upd_flops.value / (upd_ms.value * 1e-3) * 1e-12) if upd_ms.value > 0 else None
-    roofline = {"bound": "tensor", "kernel": "gemm_kernel<EPI_SUB> (Cholesky trailing update C -= P P^T, DMMA.8x8x4)",
+    roofline = {"bound": "tensor", "kernel": "tma_gemm_kernel<EpiSubTma> (Cholesky trailing update C -= P P^T; TMA-fed persistent DMMA.8x8x4)",
                 "achieved": achieved, "peak": peak, "unit": UNIT,
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
+                # (potrf N=16384, first trailing update, 1.29e11 flop, 2.08e9 algorithmic bytes):
+                "traffic": 2.644e9, "traffic_source": "profiles/r01_update_tma_ncu_summary.txt",
                 "launches_timed": int(n_upd), "kernel_ms_per_step": upd_ms.value / args.steps,
+                "scope": "rank 0's GPU (per-GPU rate against the per-GPU peak)",
                 "peak_source": "register-resident DMMA.8x8x4 issue-rate probe run live on this GPU "
                                "(smnngp_dmma_peak_tflops; MEASURED_PEAKS.json has no FP64 figure; "
                                "profiles/r01_fp64_peak.txt: 37.1 TF/s, cuBLAS Dgemm 36.0)"}
