@@ -58,3 +58,20 @@ if "lml" in which:
         print(f"lml N={n} D={d}: {t:9.3f} ms  {f/t*1e-9:7.2f} TFLOP/s  loss={out[1].item():.12f} info={info.item()}", flush=True)
         del x, y
         sm.device.release_workspaces(); torch.cuda.empty_cache()
+if "dist1" in which:
+    from smnngp_b200.distributed import DistributedLML
+    for (n, d) in ((10000, 8), (30000, 784), (60000, 784)):
+        xs, ys, *_ = pixel_data(n, d) if d > 100 else regression_data(n, d)[:2] + (None,)
+        x, y = torch.from_numpy(xs).cuda(), torch.from_numpy(ys).cuda()
+        for res in (0, 4, 8):
+            os.environ["SMNNGP_SM_RESERVE"] = str(res)
+            solver = DistributedLML(n, d, spec, "cuda")
+            r = {}
+            def run():
+                r["o"] = solver.lml(x, y, hp)
+            t = timed(run, reps=2)
+            f = n * (n + 1) * d + n ** 3 / 3 + n * n
+            print(f"stage-path P=1 reserve={res} N={n} D={d} db={solver.db}: {t:9.3f} ms {f/t*1e-9:7.2f} TFLOP/s loss={r['o'][0][1].item():.12f}", flush=True)
+            del solver
+            torch.cuda.empty_cache()
+        del x, y
