@@ -93,6 +93,13 @@ int smnngp_predict_f64(void* stream, const double* X, const double* Y, const dou
                        void* workspace, size_t workspace_bytes, double* mean_out, double* var_out,
                        int* info_dev);
 
+/* same, plus the FULL posterior covariance cov_out [T, ld_cov] = K_tt - K_td A^-1 K_dt that neural_tangents
+ * returns with compute_cov=True (spax/kernels.py:31; consumed whole only by the SVSP path, spax/models.py:43) */
+int smnngp_predict_cov_f64(void* stream, const double* X, const double* Y, const double* Xt, int64_t N, int64_t T,
+                           int64_t C, int64_t D, int n_hidden, int act, int arch, const double* hp_dev, int shift,
+                           void* workspace, size_t workspace_bytes, double* mean_out, double* var_out,
+                           double* cov_out, int64_t ld_cov, int* info_dev);
+
 /* ---- SPR.test_nll (spax/models.py:100-120) incl. Likelihood.logpdf (spax/likelihoods.py:30-33 / :52-65):
  * predictive (relative jitter) + second factorisation of K + 1e-6 (alpha/beta) I for the Student-t scale +
  * de-standardisation + mean negative log density.  nll_out_dev[1]; mean_out / var_out / logp_out are [T] and

@@ -22,7 +22,7 @@ EXPORTS = [
     "smnngp_abi_version", "smnngp_last_error", "smnngp_gram_workspace_bytes", "smnngp_gram_f64",
     "smnngp_nngp_diag_f64", "smnngp_potrf_workspace_bytes", "smnngp_potrf_f64", "smnngp_potrf_trapezoid_f64",
     "smnngp_cov_solve_workspace_bytes", "smnngp_cov_solve_f64",
-    "smnngp_lml_workspace_bytes", "smnngp_lml_f64", "smnngp_predict_workspace_bytes", "smnngp_predict_f64",
+    "smnngp_lml_workspace_bytes", "smnngp_lml_f64", "smnngp_predict_workspace_bytes", "smnngp_predict_f64", "smnngp_predict_cov_f64",
     "smnngp_test_nll_f64", "smnngp_lml_host_f64", "smnngp_predict_host_f64", "smnngp_test_nll_host_f64",
     "smnngp_host_release", "smnngp_set_panel_width", "smnngp_set_tile_variant", "smnngp_debug_occupancy",
     "smnngp_stage_qtable_f64", "smnngp_stage_gram_f64", "smnngp_stage_factor_diag_f64", "smnngp_stage_trsm_f64",
@@ -101,6 +101,8 @@ def _declare(lib):
     lib.smnngp_predict_workspace_bytes.argtypes = [_i64, _i64, _i64, _i64, _i, _i]
     lib.smnngp_predict_f64.argtypes = [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _vp, _sz,
                                        _vp, _vp, _vp]
+    lib.smnngp_predict_cov_f64.argtypes = [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _vp,
+                                           _sz, _vp, _vp, _vp, _i64, _vp]
     lib.smnngp_test_nll_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _d, _d,
                                         _vp, _sz, _vp, _vp, _vp, _vp, _vp]
     lib.smnngp_lml_host_f64.argtypes = [_vp, _vp, _i64, _i64, _i, _i, _i, _vp, _i, _vp, _vp]

@@ -345,7 +345,7 @@ size_t smnngp_predict_workspace_bytes(int64_t N, int64_t T, int64_t C, int64_t D
 static int predict_enqueue(cudaStream_t s, const double* X, const double* Y, const double* Xt, int64_t N,
                            int64_t T, int64_t C, int64_t D, int n_hidden, int act, int arch,
                            const double* hp_dev, int shift, SolveWs& w, double* mean_out, double* var_out,
-                           int* info_dev) {
+                           int* info_dev, double* cov_out = nullptr, int64_t ld_cov = 0) {
   CU(launch_qtable(s, X, D, (int)N, (int)D, n_hidden, act, arch, hp_dev, w.tab, N, w.q));
   CU(launch_scalars(s, w.q, (int)N, hp_dev, w.scal));
   CU(launch_qtable(s, Xt, D, (int)T, (int)D, n_hidden, act, arch, hp_dev, w.tab_t, T, w.q_t));
@@ -362,6 +362,18 @@ static int predict_enqueue(cudaStream_t s, const double* X, const double* Y, con
   CU(potrf_trapezoid(s, w.A, w.lda, N + T + C, N, pick_nb(N), w.linv, w.scal + SC_LOGDET, info_dev));
   CU(launch_predict_finalize(s, w.A + N * w.lda, w.lda, w.A + (N + T) * w.lda, w.lda, w.q_t, (int)T, (int)C, N,
                              info_dev, mean_out, var_out));
+  if (cov_out) {
+    // full posterior covariance K_tt - V V^T (what neural_tangents returns with compute_cov=True): Gram of the
+    // test points, then one rank-N update with the carried rows V = K_td L^-T on the same GEMM core
+    CU(enqueue_sym_gram(s, Xt, T, D, n_hidden, act, arch, hp_dev, w.tab_t, w.scal, SHIFT_NONE, 1, cov_out, ld_cov));
+    GemmParams u{};
+    u.A = w.A + N * w.lda; u.lda = w.lda;
+    u.B = w.A + N * w.lda; u.ldb = w.lda;
+    u.C = cov_out; u.ldc = ld_cov;
+    u.M = (int)T; u.N = (int)T; u.K = (int)N; u.lower = 0;
+    CU(launch_gemm_sub(s, u));
+    CU(launch_fill_nan_if_bad(s, info_dev, cov_out, T * ld_cov));
+  }
   return SMNNGP_OK;
 }
 
@@ -380,6 +392,24 @@ int smnngp_predict_f64(void* stream, const double* X, const double* Y, const dou
   CU(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
   return predict_enqueue(s, X, Y, Xt, N, T, C, D, n_hidden, act, arch, hp_dev, shift, w, mean_out, var_out,
                          info_dev);
+}
+
+int smnngp_predict_cov_f64(void* stream, const double* X, const double* Y, const double* Xt, int64_t N, int64_t T,
+                           int64_t C, int64_t D, int n_hidden, int act, int arch, const double* hp_dev, int shift,
+                           void* workspace, size_t workspace_bytes, double* mean_out, double* var_out,
+                           double* cov_out, int64_t ld_cov, int* info_dev) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!X || !Y || !Xt || !hp_dev || !mean_out || !var_out || !cov_out || !info_dev || N <= 0 || T <= 0 || C <= 0 ||
+      D <= 0 || ld_cov < T || !valid_stack(n_hidden, act, arch) || shift < 0 || shift > 3 ||
+      N + T + C > INT32_MAX || D > INT32_MAX)
+    return fail(SMNNGP_EINVAL, "smnngp_predict_cov_f64: invalid argument");
+  Carver c(workspace);
+  SolveWs w;
+  if (carve_solve(c, w, N, T, C, n_act_applications(n_hidden, arch)) > workspace_bytes || !workspace)
+    return fail(SMNNGP_EWORKSPACE, "smnngp_predict_cov_f64: workspace too small");
+  CU(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
+  return predict_enqueue(s, X, Y, Xt, N, T, C, D, n_hidden, act, arch, hp_dev, shift, w, mean_out, var_out,
+                         info_dev, cov_out, ld_cov);
 }
 
 int smnngp_test_nll_f64(void* stream, const double* X, const double* y, const double* Xt, const double* yt,

@@ -187,8 +187,9 @@ def lml(x, y, *, spec: StackSpec, hp, kind="student_t"):
     return out, info
 
 
-def predict(x, y, x_test, *, spec: StackSpec, hp, shift="eps_rel"):
-    """NNGPKernel.predict (spax/kernels.py:29-32): returns (mean [T,C], var [T] = diag(cov), info)."""
+def predict(x, y, x_test, *, spec: StackSpec, hp, shift="eps_rel", full_cov=False):
+    """NNGPKernel.predict (spax/kernels.py:29-32): returns (mean [T,C], var [T] = diag(cov), info); with
+    full_cov=True (device inputs) the second element is the full [T,T] posterior covariance."""
     lib = _lib.load()
     nh, act, arch = spec.ids()
     if isinstance(x, np.ndarray):
@@ -222,6 +223,13 @@ def predict(x, y, x_test, *, spec: StackSpec, hp, shift="eps_rel"):
     info = torch.zeros(1, dtype=torch.int32, device=x.device)
     ws_bytes = lib.smnngp_predict_workspace_bytes(n, t, c, d, nh, arch)
     ws = _workspace(ws_bytes, x.device)
+    if full_cov:
+        cov = torch.empty((t, t), dtype=torch.float64, device=x.device)
+        rc = lib.smnngp_predict_cov_f64(_stream(x.device), _p(x), _p(y), _p(xt), n, t, c, d, nh, act, arch, _p(hp),
+                                        SHIFT[shift], _p(ws), ws_bytes, _p(mean), _p(var), _p(cov), cov.stride(0),
+                                        _p(info))
+        _lib.check(rc, "predict_cov")
+        return mean, cov, info
     rc = lib.smnngp_predict_f64(_stream(x.device), _p(x), _p(y), _p(xt), n, t, c, d, nh, act, arch, _p(hp),
                                 SHIFT[shift], _p(ws), ws_bytes, _p(mean), _p(var), _p(info))
     _lib.check(rc, "predict")

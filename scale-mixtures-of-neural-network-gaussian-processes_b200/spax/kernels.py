@@ -18,16 +18,18 @@ class NNGPKernel(Module):
         """spax/kernels.py:23-27.  x2 None / same object -> symmetric path (lower tiles + mirror)."""
         return kernel_fn(x, None if (x2 is None or x2 is x) else x2, get="nngp")
 
-    def predict(self, kernel_fn, x, y, x_test, eps=1e-6):
+    def predict(self, kernel_fn, x, y, x_test, eps=1e-6, full_cov=False):
         """spax/kernels.py:29-32 (neural_tangents gradient_descent_mse_ensemble, relative diag_reg).
-        Returns (mean [T, C], var [T]); var is diag(cov), the only part the reference consumes."""
+        Returns (mean [T, C], var [T]); var is diag(cov), the only part the regression path consumes
+        (spax/likelihoods.py:31, :62).  full_cov=True returns the reference's full [T, T] covariance instead."""
         if not isinstance(kernel_fn, KernelFn):
             raise TypeError("predict needs a kernel_fn built by smnngp nt_kernels")
         import numpy as np
         if isinstance(x, np.ndarray):
             mean, var, _ = _dev.predict(x, y, x_test, spec=kernel_fn.spec, hp=kernel_fn.hp_host(eps=eps))
         else:
-            mean, var, _ = _dev.predict(x, y, x_test, spec=kernel_fn.spec, hp=kernel_fn.hp(x.device, eps=eps))
+            mean, var, _ = _dev.predict(x, y, x_test, spec=kernel_fn.spec, hp=kernel_fn.hp(x.device, eps=eps),
+                                        full_cov=full_cov)
         return mean, var
 
     def get_params(self):

@@ -183,6 +183,12 @@ def test_predict_parity(sm, n, t, d, c, act, arch):
     # variance = k_tt - ||v||^2 cancels: relative 1e-8 on the variance with an absolute floor tied to k_tt
     ktt = orc.nngp_diag(xt, **kw)
     assert np.all(np.abs(var - vref) <= LML_TOL * np.abs(vref) + 1e-13 * ktt)
+    # full covariance, as neural_tangents returns it
+    mean_c, cov, _ = sm.device.predict(torch.from_numpy(x).cuda(), torch.from_numpy(Y).cuda(), torch.from_numpy(xt).cuda(),
+                                       spec=sm.StackSpec(3, act, arch), hp=hpd, full_cov=True)
+    cov = cov.cpu().numpy()
+    assert np.abs(cov - cov_ref).max() <= LML_TOL * np.abs(cov_ref).max() + 1e-13 * ktt.max()
+    assert np.array_equal(mean_c.cpu().numpy(), mean)
     # host entry point
     hph = np.array([hp[k] for k in ("w_std", "b_std", "last_w_std", "eps", "alpha", "beta")])
     mean_h, var_h, info_h = sm.device.predict(x, Y, xt, spec=sm.StackSpec(3, act, arch), hp=hph)
