@@ -75,3 +75,12 @@ if "dist1" in which:
             del solver
             torch.cuda.empty_cache()
         del x, y
+
+if "graph" in which:
+    for (n, d) in ((2000, 8), (5000, 8), (10000, 8), (20000, 784)):
+        xs, ys, *_ = pixel_data(n, d) if d > 100 else regression_data(n, d)[:2] + (None,)
+        x, y = torch.from_numpy(xs).cuda(), torch.from_numpy(ys).cuda()
+        t0 = timed(lambda: sm.device.lml(x, y, spec=spec, hp=hp), reps=5)
+        g = sm.device.LmlGraph(n, d, spec=spec)
+        t1 = timed(lambda: g(x, y, hp), reps=5)
+        print(f"lml N={n} D={d}: eager {t0:8.3f} ms   cuda-graph replay {t1:8.3f} ms", flush=True)

@@ -187,6 +187,53 @@ def lml(x, y, *, spec: StackSpec, hp, kind="student_t"):
     return out, info
 
 
+class LmlGraph:
+    """The fused LML call captured once into a CUDA graph and replayed - the analogue of wrapping SPR.loss in
+    objax.Jit (regression/train.py:61-67): the training loop evaluates the same shapes tens of thousands of
+    times, and for N <~ 20k the ~1700 dependent small launches of the factorisation are launch-latency bound.
+    Inputs are copied into static buffers; hyper-parameters stay a device operand, so they may change between
+    replays without re-capturing."""
+
+    def __init__(self, n, d, *, spec: StackSpec, kind="student_t", device="cuda"):
+        _require_cuda()
+        self.lib = _lib.load()
+        self.spec, self.kind = spec, kind
+        nh, act, arch = spec.ids()
+        dev = torch.device(device)
+        self.x = torch.zeros((n, d), dtype=torch.float64, device=dev)
+        self.y = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.hp = torch.ones(6, dtype=torch.float64, device=dev)
+        self.out = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.info = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ws_bytes = self.lib.smnngp_lml_workspace_bytes(n, d, nh, arch)
+        self.ws = torch.empty(int(self.ws_bytes), dtype=torch.uint8, device=dev)
+        self.graph = None
+
+    def _enqueue(self):
+        nh, act, arch = self.spec.ids()
+        n, d = self.x.shape
+        rc = self.lib.smnngp_lml_f64(_stream(self.x.device), _p(self.x), _p(self.y), n, d, nh, act, arch, _p(self.hp),
+                                     KIND[self.kind], _p(self.ws), self.ws_bytes, _p(self.out), _p(self.info))
+        _lib.check(rc, "lml (graph)")
+
+    def __call__(self, x, y, hp):
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        self.hp.copy_(hp, non_blocking=True)
+        if self.graph is None:
+            s = torch.cuda.Stream(device=self.x.device)
+            s.wait_stream(torch.cuda.current_stream(self.x.device))
+            with torch.cuda.stream(s):
+                self._enqueue()                       # warm-up: function attributes, lazy module loading
+            torch.cuda.current_stream(self.x.device).wait_stream(s)
+            torch.cuda.synchronize(self.x.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._enqueue()
+        self.graph.replay()
+        return self.out, self.info
+
+
 def predict(x, y, x_test, *, spec: StackSpec, hp, shift="eps_rel", full_cov=False):
     """NNGPKernel.predict (spax/kernels.py:29-32): returns (mean [T,C], var [T] = diag(cov), info); with
     full_cov=True (device inputs) the second element is the full [T,T] posterior covariance."""

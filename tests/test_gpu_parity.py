@@ -305,3 +305,19 @@ def test_update_kernel_many_tiles_per_cta(sm, m, n, k, lower):
         c = c0.clone()
         be.update(a, b, c, bool(lower), 0, 1, 0)
         assert float((c - ref).abs().max()) <= 1e-11 * k
+
+
+def test_lml_cuda_graph_replay(sm):
+    """the fused call is enqueue-only: capture once, replay with new inputs / hyper-parameters"""
+    import torch
+    x, y, *_ = regression_data(1300, 8)
+    spec = sm.StackSpec(3, "relu", "mlp")
+    g = sm.device.LmlGraph(1300, 8, spec=spec)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    for b_std in (1e-8, 0.3):
+        hp, hpd = _hp(sm, b_std=b_std)
+        out, info = g(xd, yd, hpd)
+        ref = orc.spr_loss(x, y, eps=hp["eps"], kind="student_t", a=hp["alpha"], b=hp["beta"], **_kw(hp, 3, "relu", "mlp"))
+        assert int(info.item()) == 0 and abs(out[1].item() - ref) <= LML_TOL * abs(ref)
+        direct, _ = sm.device.lml(xd, yd, spec=spec, hp=hpd)
+        assert out[1].item() == direct[1].item()
