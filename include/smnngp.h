@@ -155,6 +155,10 @@ void smnngp_set_panel_width(int nb);
 /* tuning knob: GEMM core. 0 = TMA-fed persistent ping-pong kernel (default; cp.async 128x64 for unaligned
  * operands); 1 = cp.async 128x128, one CTA per SM; 2 = cp.async 128x64, two CTAs per SM */
 void smnngp_set_tile_variant(int v);
+/* tuning knob: 1 (default) = the fused Cholesky factors the next panel's diagonal block on an internal
+ * high-priority side stream while the bulk of the trailing update runs (fork / join with events: still
+ * enqueue-only and graph-capturable); 0 = single stream */
+void smnngp_set_lookahead(int on);
 /* resident CTAs per SM of the update kernel for a tile variant (diagnostic) */
 int smnngp_debug_occupancy(int variant);
 

@@ -19,6 +19,7 @@ hp = sm.make_hp(1.0, 1e-8, 1.0, 1e-6, 2.0, 2.0)
 spec = sm.StackSpec(3, "relu", "mlp")
 which = sys.argv[1:] or ["potrf", "gram", "lml"]
 sm._lib.load().smnngp_set_tile_variant(int(os.environ.get("TILE", "0")))
+sm._lib.load().smnngp_set_lookahead(int(os.environ.get("LOOKAHEAD", "1")))
 nbs = [int(v) for v in os.environ.get("NBS", "0").split(",")]
 if "potrf" in which:
     for n in (8192, 16384, 32768):

@@ -24,7 +24,7 @@ EXPORTS = [
     "smnngp_cov_solve_workspace_bytes", "smnngp_cov_solve_f64",
     "smnngp_lml_workspace_bytes", "smnngp_lml_f64", "smnngp_predict_workspace_bytes", "smnngp_predict_f64", "smnngp_predict_cov_f64",
     "smnngp_test_nll_f64", "smnngp_lml_host_f64", "smnngp_predict_host_f64", "smnngp_test_nll_host_f64",
-    "smnngp_host_release", "smnngp_set_panel_width", "smnngp_set_tile_variant", "smnngp_debug_occupancy",
+    "smnngp_host_release", "smnngp_set_panel_width", "smnngp_set_tile_variant", "smnngp_debug_occupancy", "smnngp_set_lookahead",
     "smnngp_stage_qtable_f64", "smnngp_stage_gram_f64", "smnngp_stage_factor_diag_f64", "smnngp_stage_trsm_f64",
     "smnngp_stage_update_f64", "smnngp_stage_sumsq_f64", "smnngp_stage_lml_finalize_f64",
     "smnngp_instr_reset", "smnngp_instr_launches", "smnngp_instr_updates", "smnngp_dmma_peak_tflops",
@@ -116,6 +116,8 @@ def _declare(lib):
     lib.smnngp_set_tile_variant.restype = None
     lib.smnngp_set_tile_variant.argtypes = [_i]
     lib.smnngp_debug_occupancy.argtypes = [_i]
+    lib.smnngp_set_lookahead.restype = None
+    lib.smnngp_set_lookahead.argtypes = [_i]
     lib.smnngp_stage_qtable_f64.argtypes = [_vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp, _i64, _vp, _vp]
     lib.smnngp_stage_gram_f64.argtypes = [_vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp, _vp, _i64, _vp, _i64, _vp,
                                           _i, _i, _vp, _i64]

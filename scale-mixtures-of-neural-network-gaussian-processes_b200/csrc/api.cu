@@ -90,7 +90,7 @@ size_t carve_solve(Carver& c, SolveWs& w, long long N, long long T, long long C,
   w.q = c.take<double>(N);
   w.tab_t = c.take<double>(na * (T > 0 ? T : 1));
   w.q_t = c.take<double>(T > 0 ? T : 1);
-  w.linv = c.take<double>(PB * PB);
+  w.linv = c.take<double>(LINV_BLOCKS * PB * PB);
   w.mean = c.take<double>((size_t)(T > 0 ? T : 1) * (C > 0 ? C : 1));
   w.var = c.take<double>(T > 0 ? T : 1);
   w.lda = round_up(N, 16);
@@ -149,6 +149,7 @@ void smnngp_set_panel_width(int nb) { g_panel_width = nb > 0 ? (nb + PB - 1) / P
 
 void smnngp_set_tile_variant(int v) { tile_variant() = (v >= 0 && v <= 2) ? v : 0; }
 int smnngp_debug_occupancy(int variant) { return debug_gemm_occupancy(variant); }
+void smnngp_set_lookahead(int on) { lookahead_mode() = on ? 1 : 0; }
 
 // ---- instrumentation for bench.py ------------------------------------------------------------------------
 void smnngp_instr_reset(int time_updates) {
@@ -224,7 +225,7 @@ size_t smnngp_potrf_workspace_bytes(int64_t N) {
   (void)N;
   Carver c(nullptr);
   c.take<double>(SC_COUNT);
-  c.take<double>(PB * PB);
+  c.take<double>(LINV_BLOCKS * PB * PB);
   return c.total();
 }
 
@@ -235,7 +236,7 @@ int smnngp_potrf_trapezoid_f64(void* stream, double* A, int64_t M, int64_t N, in
     return fail(SMNNGP_EINVAL, "smnngp_potrf_trapezoid_f64: invalid argument");
   Carver c(workspace);
   double* scal = c.take<double>(SC_COUNT);
-  double* linv = c.take<double>(PB * PB);
+  double* linv = c.take<double>(LINV_BLOCKS * PB * PB);
   if (c.total() > workspace_bytes || !workspace)
     return fail(SMNNGP_EWORKSPACE, "smnngp_potrf_trapezoid_f64: workspace too small");
   CU(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
@@ -260,7 +261,7 @@ int smnngp_potrf_f64(void* stream, double* A, int64_t N, int64_t ld, int* info_d
 size_t smnngp_cov_solve_workspace_bytes(int64_t N) {
   Carver c(nullptr);
   c.take<double>(SC_COUNT);
-  c.take<double>(PB * PB);
+  c.take<double>(LINV_BLOCKS * PB * PB);
   c.take<double>((size_t)(N + 1) * round_up(N, 16));
   return c.total();
 }
@@ -282,7 +283,7 @@ int smnngp_cov_solve_f64(void* stream, const double* cov, int64_t N, int64_t ld,
     return fail(SMNNGP_EINVAL, "smnngp_cov_solve_f64: invalid argument (N must be < 65535 on this entry point)");
   Carver c(workspace);
   double* scal = c.take<double>(SC_COUNT);
-  double* linv = c.take<double>(PB * PB);
+  double* linv = c.take<double>(LINV_BLOCKS * PB * PB);
   const long long lda = round_up(N, 16);
   double* A = c.take<double>((size_t)(N + 1) * lda);
   if (c.total() > workspace_bytes || !workspace)

@@ -407,10 +407,10 @@ cudaError_t launch_potf2_trtri(cudaStream_t s, double* A, long long lda, int w, 
   return cudaGetLastError();
 }
 
-cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long Mtot, long long N, int NB,
-                            double* Linv_base, double* logdet, int* info, long long linv_stride) {
-  if (NB < PB) NB = PB;
-  NB = (NB / PB) * PB;
+// Plain right-looking two-level factorisation on ONE stream (also the building block of the look-ahead variant,
+// where it factors the NB x NB diagonal blocks).
+static cudaError_t potrf_serial(cudaStream_t s, double* A, long long lda, long long Mtot, long long N, int NB,
+                                double* Linv_base, double* logdet, int* info, long long linv_stride, int gcol_base) {
   cudaError_t e;
   for (long long c0 = 0; c0 < N; c0 += NB) {
     const long long c1 = (c0 + NB < N) ? c0 + NB : N;
@@ -418,7 +418,7 @@ cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long 
       const long long j1 = (j0 + PB < N) ? j0 + PB : N;
       const int w = (int)(j1 - j0);
       double* Linv_ws = Linv_base + (j0 / PB) * linv_stride;
-      e = launch_potf2_trtri(s, A + j0 * lda + j0, lda, w, Linv_ws, logdet, info, (int)j0);
+      e = launch_potf2_trtri(s, A + j0 * lda + j0, lda, w, Linv_ws, logdet, info, gcol_base + (int)j0);
       if (e != cudaSuccess) return e;
       if (Mtot > j1) {
         GemmParams t{};   // panel rows <- panel rows * inv(L_jj)^T   (in place: one CTA owns whole rows)
@@ -455,6 +455,120 @@ cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long 
       if (e != cudaSuccess) return e;
     }
   }
+  return cudaSuccess;
+}
+
+// ---- look-ahead ---------------------------------------------------------------------------------------------
+// Per outer panel p:   side stream : factor the NB x NB diagonal block (latency-bound chain of small kernels)
+//                      main stream : TRSM of the rows below, update of the NEXT panel's block column (update_a),
+//                                    then the bulk of the trailing matrix (update_b).
+// The diagonal block of panel p+1 only needs update_a(p), so its chain runs under update_b(p).  The persistent
+// update kernel would otherwise hold every SM, so for trailing matrices small enough that the chain matters
+// update_b leaves a few SMs free.
+namespace {
+struct LookaheadCtx {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_diag = nullptr, ev_a = nullptr;
+  bool ok = false;
+};
+LookaheadCtx g_la[64];
+
+LookaheadCtx* lookahead_ctx() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  LookaheadCtx& c = g_la[dev];
+  if (!c.ok) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c.ev_diag, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c.ev_a, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    c.ok = true;
+  }
+  return &c;
+}
+}  // namespace
+
+int& lookahead_mode() {
+  static int v = 1;
+  return v;
+}
+
+cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long Mtot, long long N, int NB,
+                            double* Linv_base, double* logdet, int* info, long long linv_stride) {
+  if (NB < PB) NB = PB;
+  NB = (NB / PB) * PB;
+  if (NB > LINV_BLOCKS * PB) NB = LINV_BLOCKS * PB;
+  LookaheadCtx* la = (lookahead_mode() != 0 && linv_stride == 0 && N > NB) ? lookahead_ctx() : nullptr;
+  if (la == nullptr) return potrf_serial(s, A, lda, Mtot, N, NB, Linv_base, logdet, info, linv_stride, 0);
+
+#define LA_CK(call)                 \
+  do {                              \
+    cudaError_t e__ = (call);       \
+    if (e__ != cudaSuccess) return e__; \
+  } while (0)
+  const long long ls = (long long)PB * PB;          // one inverse block per 128 columns of the current panel
+  LA_CK(cudaEventRecord(la->ev_fork, s));
+  LA_CK(cudaStreamWaitEvent(la->side, la->ev_fork, 0));
+  for (long long c0 = 0; c0 < N; c0 += NB) {
+    const long long c1 = (c0 + NB < N) ? c0 + NB : N;
+    const int w = (int)(c1 - c0);
+    // side: diagonal block (w x w) with its block inverses
+    LA_CK(potrf_serial(la->side, A + c0 * lda + c0, lda, w, w, NB, Linv_base, logdet, info, ls, (int)c0));
+    LA_CK(cudaEventRecord(la->ev_diag, la->side));
+    LA_CK(cudaStreamWaitEvent(s, la->ev_diag, 0));
+    // main: rows below the diagonal block <- rows * L_pp^-T by 128-block substitution
+    const long long m = Mtot - c1;
+    if (m > 0) {
+      double* R = A + c1 * lda + c0;
+      for (long long j0 = 0; j0 < w; j0 += PB) {
+        const long long j1 = (j0 + PB < w) ? j0 + PB : w;
+        GemmParams t{};
+        t.A = R + j0; t.lda = lda;
+        t.B = Linv_base + (j0 / PB) * ls; t.ldb = PB;
+        t.C = R + j0; t.ldc = lda;
+        t.M = (int)m; t.N = (int)(j1 - j0); t.K = (int)(j1 - j0); t.lower = 0;
+        LA_CK(launch_gemm_store(s, t));
+        if (j1 < w) {
+          GemmParams u{};
+          u.A = R + j0; u.lda = lda;
+          u.B = A + (c0 + j1) * lda + c0 + j0; u.ldb = lda;
+          u.C = R + j1; u.ldc = lda;
+          u.M = (int)m; u.N = (int)(w - j1); u.K = (int)(j1 - j0); u.lower = 0;
+          LA_CK(launch_gemm_sub(s, u));
+        }
+      }
+    }
+    if (c1 >= N) break;
+    const long long na = (c1 + NB < N) ? NB : N - c1;       // next panel's block column first
+    if (instr().time_updates) {
+      const double nsq = (double)(N - c1), extra = (double)(Mtot - N);
+      instr_begin_update(s, (nsq * (nsq + 1.0) + 2.0 * extra * nsq) * (double)w);
+    }
+    {
+      GemmParams u{};
+      u.A = A + c1 * lda + c0; u.lda = lda;
+      u.B = A + c1 * lda + c0; u.ldb = lda;
+      u.C = A + c1 * lda + c1; u.ldc = lda;
+      u.M = (int)(Mtot - c1); u.N = (int)na; u.K = w; u.lower = 1;
+      LA_CK(launch_gemm_sub(s, u));
+    }
+    LA_CK(cudaEventRecord(la->ev_a, s));
+    LA_CK(cudaStreamWaitEvent(la->side, la->ev_a, 0));
+    const long long cb = c1 + na;
+    if (cb < N) {
+      GemmParams u{};
+      u.A = A + cb * lda + c0; u.lda = lda;
+      u.B = A + cb * lda + c0; u.ldb = lda;
+      u.C = A + cb * lda + cb; u.ldc = lda;
+      u.M = (int)(Mtot - cb); u.N = (int)(N - cb); u.K = w; u.lower = 1;
+      u.sm_reserve = (N - cb < 24000) ? 8 : 0;
+      LA_CK(launch_gemm_sub(s, u));
+    }
+    if (instr().time_updates) instr_end_update(s);
+  }
+#undef LA_CK
   return cudaSuccess;
 }
 

@@ -6,10 +6,13 @@ namespace smnngp {
 
 constexpr int HP_W = 0, HP_B = 1, HP_V = 2, HP_EPS = 3, HP_ALPHA = 4, HP_BETA = 5, HP_COUNT = 6;
 constexpr int PB = 128;  // diagonal block / inner panel width of the Cholesky
+constexpr int LINV_BLOCKS = 4;   // inverse diagonal blocks kept per outer panel (NB <= 512)
 
 // 0 = TilePair (128x64, two CTAs per SM; default), 1 = TileBig (128x128, one CTA per SM)
 int& tile_variant();
 int debug_gemm_occupancy(int variant);
+// 1 (default): the fused factorisation runs the next panel's diagonal block on a side stream (look-ahead)
+int& lookahead_mode();
 
 inline int n_act_applications(int n_hidden, int arch) { return arch == ARCH_RESNET ? n_hidden + 1 : n_hidden; }
 

@@ -47,7 +47,7 @@ int smnngp_stage_factor_diag_f64(void* stream, double* A, int64_t lda, int64_t w
   if (!A || !linv_blocks || !logdet_dev || !info_dev || w <= 0) return SMNNGP_EINVAL;
   (void)gcol0;
   return fail_stage(potrf_trapezoid(s, A, lda, w, w, (int)((w + PB - 1) / PB * PB), linv_blocks, logdet_dev, info_dev,
-                                    (long long)PB * PB));
+                                    (long long)PB * PB));   // single panel: serial path, one inverse block per 128 columns
 }
 
 // R [m, w] <- R * L^-T by 128-block substitution with the factor L [w, w] (ldl) and its block inverses
