@@ -110,6 +110,20 @@ int smnngp_test_nll_f64(void* stream, const double* X, const double* y, const do
                         double* nll_out_dev, double* mean_out, double* var_out, double* logp_out,
                         int* info_dev);
 
+/* ---- posterior draw stage of the classification / ensemble configuration.
+ * mean [T, C]; var [T] (shared by the classes, var_per_class = 0) or [C, T] (var_per_class = 1); kind STUDENT_T:
+ * InverseGammaPrior.sample_f_iid (spax/priors.py:60-68), f = mean + sqrt((b/a) var) t_{2a}; kind GAUSS:
+ * GaussianPrior.sample_f_iid (spax/priors.py:30-36).  Counter-based Philox stream keyed by `seed`.
+ *   sample_f_iid : materialises out [C, T, S]
+ *   draw_metrics : the same draws, never written: per-point log-likelihood of the true label
+ *                  logsumexp_s(log_softmax_c f)[label] - log S  (spax/utils.py:61-66), predicted class
+ *                  argmax_c logsumexp_s log_softmax (spax/utils.py:69-74); out_dev[2] = { nll, correct count } */
+int smnngp_sample_f_iid_f64(void* stream, const double* mean, const double* var, int var_per_class, int64_t T,
+                            int64_t C, int64_t S, const double* hp_dev, int kind, uint64_t seed, double* out);
+int smnngp_draw_metrics_f64(void* stream, const double* mean, const double* var, int var_per_class,
+                            const int* label, int64_t T, int64_t C, int64_t S, const double* hp_dev, int kind,
+                            uint64_t seed, double* ll_per_test, int* pred, double* out_dev);
+
 /* ---- stage-level entry points (multi-GPU driver: one process per GPU interleaves these with NCCL collectives;
  * same kernels as the fused calls).  Layout and algorithm: DESIGN.md section 7.
  *   qtable      per-row layer tables (+ optional scalar block: tr(K)/N and the shift values)

@@ -26,7 +26,8 @@ from scipy.special import gammaln
 __all__ = [
     "softplus", "softplus_inverse", "nngp_gram", "nngp_diag", "jitter", "multivariate_t_logpdf",
     "multivariate_normal_logpdf", "prior_logpdf", "spr_loss", "nt_predict", "student_t_logpdf",
-    "normal_logpdf", "likelihood_logpdf", "spr_test_nll", "sample_f_iid_moments",
+    "normal_logpdf", "likelihood_logpdf", "spr_test_nll", "sample_f_iid_moments", "test_log_likelihood",
+    "get_correct_count",
 ]
 
 ACTS = ("relu", "erf")
@@ -293,3 +294,31 @@ def sample_f_iid_moments(mean, cov, *, a, b):
     diagonal of (b/a) cov.  Returns (loc, sigma, df) - the distribution, not draws."""
     sigma = np.sqrt(np.diagonal(b / a * cov, axis1=-2, axis2=-1))
     return mean, sigma, 2 * a
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Monte-Carlo classification metrics on draws sampled_f [C, B, S]: spax/utils.py:47-74
+# ----------------------------------------------------------------------------------------------------------
+def _log_softmax0(f):
+    m = f.max(axis=0, keepdims=True)
+    return f - (m + np.log(np.exp(f - m).sum(axis=0, keepdims=True)))
+
+
+def _logsumexp(x, axis):
+    m = x.max(axis=axis, keepdims=True)
+    return (m + np.log(np.exp(x - m).sum(axis=axis, keepdims=True))).squeeze(axis)
+
+
+def test_log_likelihood(sampled_f, label):
+    """spax/utils.py:61-66."""
+    num_samples = sampled_f.shape[2]
+    lsm = _log_softmax0(sampled_f)                                       # [C, B, S]
+    true = np.take_along_axis(lsm, np.asarray(label)[None, :, None].repeat(num_samples, axis=2), axis=0)[0]
+    return float(np.mean(_logsumexp(true, 1) - np.log(num_samples)))
+
+
+def get_correct_count(sampled_f, label):
+    """spax/utils.py:69-74."""
+    lsm = _log_softmax0(sampled_f)
+    y_pred = np.argmax(_logsumexp(lsm, 2), axis=0)
+    return int(np.sum(y_pred == np.asarray(label)))

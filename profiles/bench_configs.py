@@ -82,3 +82,18 @@ if "c5" in which:
                      tflops=(n * (n + 1) * 784 + n ** 3 / 3 + n * n) / tm * 1e-9)
         del xd, yd
         sm.device.release_workspaces(); torch.cuda.empty_cache()
+
+if "c4draw" in which:
+    # config 4 end to end: predictive (shared factorisation) -> S draws per (class, test point) -> NLL / accuracy
+    n, d, t, c = 20000, 3072, 10000, 10
+    rng = np.random.default_rng(10)
+    x = rng.standard_normal((n, d)); xt = rng.standard_normal((t, d))
+    lab = rng.integers(0, c, n); Y = np.eye(c)[lab] - 1.0 / c
+    labt = rng.integers(0, c, t)
+    xd, Yd, xtd = torch.from_numpy(x).cuda(), torch.from_numpy(Y).cuda(), torch.from_numpy(xt).cuda()
+    mean, var, info = sm.device.predict(xd, Yd, xtd, spec=spec, hp=hpd)
+    for S in (100, 1000, 10000):
+        r = {}
+        tm = timed(lambda: r.__setitem__("m", sm.device.draw_metrics(mean, var, labt, hp=hpd, num_samples=S, seed=10)), reps=2)
+        emit(config="C4-draws", T=t, C=c, S=S, draw_metrics_ms=tm, gdraws_per_s=t * c * S / tm * 1e-6,
+             nll=r["m"][0].item(), correct=int(r["m"][1].item()))

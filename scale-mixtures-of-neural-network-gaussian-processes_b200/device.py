@@ -327,3 +327,38 @@ def test_nll(x, y, x_test, y_test, y_mean, y_std, *, spec: StackSpec, hp, kind="
 
 def set_panel_width(nb: int):
     _lib.load().smnngp_set_panel_width(int(nb))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# posterior draw stage (classification / ensemble configuration)
+def sample_f_iid(mean, var, *, hp, kind="student_t", num_samples, seed=0):
+    """Prior.sample_f_iid (spax/priors.py:30-36, :60-68).  mean [T, C] (NNGPKernel.predict layout), var [T] or
+    [C, T]  ->  draws [C, T, S]."""
+    _require_cuda()
+    lib = _lib.load()
+    mean = _f64(mean)
+    var = _f64(var, mean.device)
+    t, c = mean.shape
+    out = torch.empty((c, t, int(num_samples)), dtype=torch.float64, device=mean.device)
+    rc = lib.smnngp_sample_f_iid_f64(_stream(mean.device), _p(mean), _p(var), 1 if var.ndim == 2 else 0, t, c,
+                                     int(num_samples), _p(hp), KIND[kind], int(seed), _p(out))
+    _lib.check(rc, "sample_f_iid")
+    return out
+
+
+def draw_metrics(mean, var, label, *, hp, kind="student_t", num_samples, seed=0):
+    """Fused draw -> test_log_likelihood / get_correct_count (spax/utils.py:61-74) without materialising the
+    [C, T, S] draws.  Returns (nll, correct_count, ll_per_test [T], pred [T])."""
+    _require_cuda()
+    lib = _lib.load()
+    mean = _f64(mean)
+    var = _f64(var, mean.device)
+    label = torch.as_tensor(label, device=mean.device).to(torch.int32).contiguous()
+    t, c = mean.shape
+    ll = torch.empty(t, dtype=torch.float64, device=mean.device)
+    pred = torch.empty(t, dtype=torch.int32, device=mean.device)
+    out = torch.empty(2, dtype=torch.float64, device=mean.device)
+    rc = lib.smnngp_draw_metrics_f64(_stream(mean.device), _p(mean), _p(var), 1 if var.ndim == 2 else 0, _p(label), t,
+                                     c, int(num_samples), _p(hp), KIND[kind], int(seed), _p(ll), _p(pred), _p(out))
+    _lib.check(rc, "draw_metrics")
+    return out[0], out[1], ll, pred

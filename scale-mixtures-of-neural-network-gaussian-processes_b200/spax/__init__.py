@@ -4,3 +4,4 @@ from .models import SPR
 from .utils import jitter, multivariate_t_logpdf, multivariate_normal_logpdf
 from .base import Module, TrainVar, ConstraintTrainVar
 from .bijectors import positive
+from .priors import Prior, GaussianPrior, InverseGammaPrior

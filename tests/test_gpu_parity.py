@@ -321,3 +321,38 @@ def test_lml_cuda_graph_replay(sm):
         assert int(info.item()) == 0 and abs(out[1].item() - ref) <= LML_TOL * abs(ref)
         direct, _ = sm.device.lml(xd, yd, spec=spec, hp=hpd)
         assert out[1].item() == direct[1].item()
+
+
+@pytest.mark.parametrize("kind", ["student_t", "gauss"])
+def test_draw_stage(sm, kind):
+    """sample_f_iid (spax/priors.py:30-36, :60-68) + test_log_likelihood / get_correct_count (spax/utils.py:61-74):
+    distribution of the draws, and the fused metrics kernel against the oracle evaluated on the SAME draws."""
+    import torch
+    import scipy.stats
+    rng = np.random.default_rng(7)
+    T, C, S = 37, 10, 4000
+    mean = rng.standard_normal((T, C))
+    var = rng.uniform(0.05, 2.0, T)
+    label = rng.integers(0, C, T)
+    a, b = 2.5, 1.5
+    hpd = sm.make_hp(1.0, 0.0, 1.0, 1e-6, a, b)
+    md, vd = torch.from_numpy(mean).cuda(), torch.from_numpy(var).cuda()
+    f = sm.device.sample_f_iid(md, vd, hp=hpd, kind=kind, num_samples=S, seed=1234).cpu().numpy()   # [C, T, S]
+    assert f.shape == (C, T, S) and np.isfinite(f).all()
+    scale = np.sqrt((b / a if kind == "student_t" else 1.0) * var)
+    z = (f - mean.T[:, :, None]) / scale[None, :, None]
+    dist = scipy.stats.t(2 * a) if kind == "student_t" else scipy.stats.norm()
+    ks = scipy.stats.kstest(z.ravel()[:200000], dist.cdf)
+    assert ks.pvalue > 1e-3, ks
+    assert abs(np.corrcoef(z[0, 0], z[1, 0])[0, 1]) < 0.08           # iid across classes
+    assert abs(np.corrcoef(z[0, 0], z[0, 1])[0, 1]) < 0.08           # ... and across test points
+    nll, correct, ll, pred = sm.device.draw_metrics(md, vd, label, hp=hpd, kind=kind, num_samples=S, seed=1234)
+    ref_nll = -orc.test_log_likelihood(f, label)
+    ref_correct = orc.get_correct_count(f, label)
+    assert abs(nll.item() - ref_nll) <= 1e-10 * abs(ref_nll)
+    assert int(correct.item()) == ref_correct
+    # the mirrored prior class
+    from smnngp_b200.spax import InverseGammaPrior, GaussianPrior
+    prior = InverseGammaPrior(a, b) if kind == "student_t" else GaussianPrior()
+    f2 = prior.sample_f_iid(1234, md.T.contiguous(), vd, S).cpu().numpy()
+    assert np.array_equal(f2, f)
