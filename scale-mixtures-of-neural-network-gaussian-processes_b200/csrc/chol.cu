@@ -172,19 +172,28 @@ cudaError_t launch_gemm_t(cudaStream_t s, const GemmParams& p) {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int PF_THREADS = 256;
 constexpr int PF_WARPS = PF_THREADS / 32;
-constexpr int DB = 32;                 // register-resident diagonal block
+#ifndef SMNNGP_DB
+#define SMNNGP_DB 16
+#endif
+constexpr int DB = SMNNGP_DB;          // register-resident diagonal block (16: ~400 instructions, stays in the
+                                       // instruction cache; the 32-wide version was instruction-fetch bound)
+constexpr int KS = DB / 4;             // k4-steps per block
+constexpr int NT = DB / 8;             // 8-wide tiles per block
+constexpr int NBLK = PB / DB;
 constexpr int GLD = PB + 4;            // 132: (4 * row + k) mod 16 distinct over a half-warp's 4 rows x 4 k
-constexpr int MLD = DB + 4;            // 36: same property
-constexpr int PF_SMEM_BYTES = (PB * GLD + 4 * DB * MLD + 64) * 8;
+constexpr int MLD = DB + 4;            // 20 / 36: same property
+constexpr int PF_SMEM_BYTES = (PB * GLD + NBLK * DB * MLD + 64) * 8;
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// warp 0, lane = row: factor the 32x32 block at Gbb (lower part valid), write L back (lower) and inv(L) to M.
-__device__ __forceinline__ void diag32_factor_invert(double* __restrict__ Gbb, double* __restrict__ M, int lane,
-                                                     int col_base, int& bad) {
+// warp 0, lane = row (lanes >= DB idle along): factor the DB x DB block at Gbb (lower part valid), write L back
+// (lower) and inv(L) to M.
+__device__ __forceinline__ void diag_factor_invert(double* __restrict__ Gbb, double* __restrict__ M, int lane,
+                                                   int col_base, int& bad) {
+  const int row = lane < DB ? lane : DB - 1;
   double a[DB];
 #pragma unroll
-  for (int c = 0; c < DB; c++) a[c] = Gbb[lane * GLD + c];
+  for (int c = 0; c < DB; c++) a[c] = Gbb[row * GLD + c];
 #pragma unroll
   for (int j = 0; j < DB; j++) {
     double d = shfl_d(a[j], j);
@@ -198,9 +207,11 @@ __device__ __forceinline__ void diag32_factor_invert(double* __restrict__ Gbb, d
 #pragma unroll
     for (int c = j + 1; c < DB; c++) a[c] = fma(-l, shfl_d(l, c), a[c]);
   }
+  if (lane < DB) {
 #pragma unroll
-  for (int c = 0; c < DB; c++)
-    if (c <= lane) Gbb[lane * GLD + c] = a[c];
+    for (int c = 0; c < DB; c++)
+      if (c <= lane) Gbb[lane * GLD + c] = a[c];
+  }
   __syncwarp();
   // inverse, lane = column c: x_i = (delta_ic - sum_{k=c}^{i-1} L_ik x_k) / L_ii   (L_ik: broadcast reads)
   double x[DB];
@@ -215,18 +226,14 @@ __device__ __forceinline__ void diag32_factor_invert(double* __restrict__ Gbb, d
     const double v = (s0 + s1) / Gbb[i * GLD + i];
     x[i] = (i >= lane) ? v : 0.0;     // rows above the column's diagonal stay exactly zero
   }
+  if (lane < DB) {
 #pragma unroll
-  for (int i = 0; i < DB; i++) M[i * MLD + lane] = x[i];
+    for (int i = 0; i < DB; i++) M[i * MLD + lane] = x[i];
+  }
 }
 
-// acc(8x8) += sum over nks k4-steps of A[row, k] * B[col, k]; A, B K-contiguous (element (r, k) at p[r*ld + k])
-__device__ __forceinline__ void tile_nt(double (&acc)[2], const double* __restrict__ A, int lda,
-                                        const double* __restrict__ B, int ldb, int nks, int lane) {
-  const double* ap = A + (lane >> 2) * lda + (lane & 3);
-  const double* bp = B + (lane >> 2) * ldb + (lane & 3);
-  for (int ks = 0; ks < nks; ks++) dmma8x8x4(acc, ap[ks * 4], bp[ks * 4]);
-}
-// same with B k-major: element (k, col) at B[k*ldb + col]
+// acc(8x8) += sum over nks k4-steps of A[row, k] * B[k, col]; A K-contiguous, B k-major (element (k, col) at
+// B[k*ldb + col])
 __device__ __forceinline__ void tile_nn(double (&acc)[2], const double* __restrict__ A, int lda,
                                         const double* __restrict__ B, int ldb, int nks, int lane) {
   const double* ap = A + (lane >> 2) * lda + (lane & 3);
@@ -239,62 +246,71 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
                    double* __restrict__ logdet, int* __restrict__ info, int gcol0) {
   extern __shared__ __align__(16) double sm[];
   double* G = sm;                          // [128][132]
-  double* Mi = G + PB * GLD;               // 4 x [32][36] inverse diagonal blocks
-  double* red = Mi + 4 * DB * MLD;
+  double* Mi = G + PB * GLD;               // NBLK x [DB][MLD] inverse diagonal blocks
+  double* red = Mi + NBLK * DB * MLD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nblk = (w + DB - 1) / DB;
   const int wp = nblk * DB;                // padded size (identity padding)
 
-  for (int idx = tid; idx < PB * PB; idx += PF_THREADS) {
-    int i = idx >> 7, c = idx & (PB - 1);
-    double g = 0.0;
-    if (i < w && c <= i) g = A[(long long)i * lda + c];
-    else if (i == c) g = 1.0;
-    G[i * GLD + c] = g;
+  // stage the lower triangle (the upper part of G is scratch for the inverse assembly and must start at zero)
+  for (int idx = tid; idx < wp * (PB / 2); idx += PF_THREADS) {
+    const int i = idx >> 6, c = (idx & 63) * 2;
+    double2 g = make_double2(0.0, 0.0);
+    if (i < w && c <= i) {
+      const double* src = A + (long long)i * lda + c;
+      g.x = src[0];
+      if (c + 1 <= i) g.y = src[1];
+    }
+    if (i >= w) {
+      if (c == i) g.x = 1.0;
+      if (c + 1 == i) g.y = 1.0;
+    }
+    G[i * GLD + c] = g.x;
+    G[i * GLD + c + 1] = g.y;
   }
   __syncthreads();
 
   int bad = 0;
   for (int b = 0; b < nblk; b++) {
     const int b0 = b * DB;
-    if (warp == 0) diag32_factor_invert(G + b0 * GLD + b0, Mi + b * DB * MLD, lane, b0, bad);
+    if (warp == 0) diag_factor_invert(G + b0 * GLD + b0, Mi + b * DB * MLD, lane, b0, bad);
     __syncthreads();
     const int r_first = b0 + DB;
     const int nstrips = (wp - r_first) / 8;
     // panel: rows below, P = S_ib * inv(L_bb)^T   (a warp owns whole 8-row strips -> in place)
     for (int s = warp; s < nstrips; s += PF_WARPS) {
       const int r0 = r_first + s * 8;
-      double af[8];
+      double af[KS];
       const double* ap = G + (r0 + (lane >> 2)) * GLD + b0 + (lane & 3);
 #pragma unroll
-      for (int ks = 0; ks < 8; ks++) af[ks] = ap[ks * 4];
-      double acc[4][2];
+      for (int ks = 0; ks < KS; ks++) af[ks] = ap[ks * 4];
+      double acc[NT][2];
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) {
+      for (int nt = 0; nt < NT; nt++) {
         acc[nt][0] = acc[nt][1] = 0.0;
         const double* bp = Mi + b * DB * MLD + (nt * 8 + (lane >> 2)) * MLD + (lane & 3);
 #pragma unroll
-        for (int ks = 0; ks < 8; ks++)
+        for (int ks = 0; ks < KS; ks++)
           if (ks <= 2 * nt + 1) dmma8x8x4(acc[nt], af[ks], bp[ks * 4]);   // inv(L) is lower triangular
       }
       __syncwarp();
       double* op = G + (r0 + (lane >> 2)) * GLD + b0 + (lane & 3) * 2;
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) { op[nt * 8] = acc[nt][0]; op[nt * 8 + 1] = acc[nt][1]; }
+      for (int nt = 0; nt < NT; nt++) { op[nt * 8] = acc[nt][0]; op[nt * 8 + 1] = acc[nt][1]; }
     }
     __syncthreads();
     // trailing update: S_ic -= P_i P_c^T for r_first <= c-tile <= row strip
     for (int s = warp; s < nstrips; s += PF_WARPS) {
       const int r0 = r_first + s * 8;
-      double af[8];
+      double af[KS];
       const double* ap = G + (r0 + (lane >> 2)) * GLD + b0 + (lane & 3);
 #pragma unroll
-      for (int ks = 0; ks < 8; ks++) af[ks] = ap[ks * 4];
+      for (int ks = 0; ks < KS; ks++) af[ks] = ap[ks * 4];
       for (int c0 = r_first; c0 <= r0; c0 += 8) {
         double acc[2] = {0.0, 0.0};
         const double* bp = G + (c0 + (lane >> 2)) * GLD + b0 + (lane & 3);
 #pragma unroll
-        for (int ks = 0; ks < 8; ks++) dmma8x8x4(acc, af[ks], bp[ks * 4]);
+        for (int ks = 0; ks < KS; ks++) dmma8x8x4(acc, af[ks], bp[ks * 4]);
         double* cp = G + (r0 + (lane >> 2)) * GLD + c0 + (lane & 3) * 2;
         cp[0] -= acc[0];
         cp[1] -= acc[1];
@@ -306,15 +322,15 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
   // ---- inverse assembly: X_ik (i > k) is kept at block position (k, i) of G (upper triangle, untransposed)
   for (int dist = 1; dist < nblk; dist++) {
     const int npairs = nblk - dist;
-    // phase A: T_ik = sum_{m=k}^{i-1} L_im X_mk ; 16 output tiles per pair
-    for (int u = warp; u < npairs * 16; u += PF_WARPS) {
-      const int k = u >> 4, t = u & 15, i = k + dist;
-      const int tr = (t >> 2) * 8, tc = (t & 3) * 8;
+    // phase A: T_ik = sum_{m=k}^{i-1} L_im X_mk ; NT*NT output tiles per pair
+    for (int u = warp; u < npairs * NT * NT; u += PF_WARPS) {
+      const int k = u / (NT * NT), t = u % (NT * NT), i = k + dist;
+      const int tr = (t / NT) * 8, tc = (t % NT) * 8;
       double acc[2] = {0.0, 0.0};
       for (int m = k; m < i; m++) {
         const double* Lim = G + (i * DB + tr) * GLD + m * DB;
-        if (m == k) tile_nn(acc, Lim, GLD, Mi + k * DB * MLD + tc, MLD, 8, lane);
-        else tile_nn(acc, Lim, GLD, G + (k * DB) * GLD + m * DB + tc, GLD, 8, lane);
+        if (m == k) tile_nn(acc, Lim, GLD, Mi + k * DB * MLD + tc, MLD, KS, lane);
+        else tile_nn(acc, Lim, GLD, G + (k * DB) * GLD + m * DB + tc, GLD, KS, lane);
       }
       // T is written to its final place (k, i); nobody reads that block in this phase
       double* tp = G + (k * DB + tr + (lane >> 2)) * GLD + i * DB + tc + (lane & 3) * 2;
@@ -323,24 +339,24 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
     }
     __syncthreads();
     // phase B: X_ik = -inv(L_ii) T_ik in place; a warp owns an 8-column strip of one block
-    for (int u = warp; u < npairs * 4; u += PF_WARPS) {
-      const int k = u >> 2, tc = (u & 3) * 8, i = k + dist;
+    for (int u = warp; u < npairs * NT; u += PF_WARPS) {
+      const int k = u / NT, tc = (u % NT) * 8, i = k + dist;
       double* T = G + (k * DB) * GLD + i * DB + tc;
-      double bf[8];
+      double bf[KS];
 #pragma unroll
-      for (int ks = 0; ks < 8; ks++) bf[ks] = T[(ks * 4 + (lane & 3)) * GLD + (lane >> 2)];
-      double acc[4][2];
+      for (int ks = 0; ks < KS; ks++) bf[ks] = T[(ks * 4 + (lane & 3)) * GLD + (lane >> 2)];
+      double acc[NT][2];
 #pragma unroll
-      for (int rt = 0; rt < 4; rt++) {
+      for (int rt = 0; rt < NT; rt++) {
         acc[rt][0] = acc[rt][1] = 0.0;
         const double* ap = Mi + i * DB * MLD + (rt * 8 + (lane >> 2)) * MLD + (lane & 3);
 #pragma unroll
-        for (int ks = 0; ks < 8; ks++)
+        for (int ks = 0; ks < KS; ks++)
           if (ks <= 2 * rt + 1) dmma8x8x4(acc[rt], ap[ks * 4], bf[ks]);
       }
       __syncwarp();
 #pragma unroll
-      for (int rt = 0; rt < 4; rt++) {
+      for (int rt = 0; rt < NT; rt++) {
         double* op = T + (rt * 8 + (lane >> 2)) * GLD + (lane & 3) * 2;
         op[0] = -acc[rt][0];
         op[1] = -acc[rt][1];
@@ -349,18 +365,29 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
     __syncthreads();
   }
 
-  for (int idx = tid; idx < PB * PB; idx += PF_THREADS) {
-    const int i = idx >> 7, c = idx & (PB - 1);
-    if (i < w && c <= i) A[(long long)i * lda + c] = G[i * GLD + c];
-    double v = 0.0;
-    if (i < wp && c <= i) {
-      const int bi = i / DB, bc = c / DB;
-      v = (bi == bc) ? Mi[bi * DB * MLD + (i - bi * DB) * MLD + (c - bc * DB)]
-                     : G[(bc * DB + (i - bi * DB)) * GLD + bi * DB + (c - bc * DB)];
-    } else if (i == c) {
-      v = 1.0;
+  // write back: L (lower part only) and inv(L) (full 128 x 128: zero above the diagonal, identity padded)
+  for (int idx = tid; idx < PB * (PB / 2); idx += PF_THREADS) {
+    const int i = idx >> 6, c = (idx & 63) * 2;
+    if (i < w && c <= i) {
+      double* dst = A + (long long)i * lda + c;
+      dst[0] = G[i * GLD + c];
+      if (c + 1 <= i) dst[1] = G[i * GLD + c + 1];
     }
-    Linv[idx] = v;
+    double2 v = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int cc = c + e;
+      double x = 0.0;
+      if (i < wp && cc <= i) {
+        const int bi = i / DB, bc = cc / DB;
+        x = (bi == bc) ? Mi[bi * DB * MLD + (i - bi * DB) * MLD + (cc - bc * DB)]
+                       : G[(bc * DB + (i - bi * DB)) * GLD + bi * DB + (cc - bc * DB)];
+      } else if (i == cc) {
+        x = 1.0;
+      }
+      if (e == 0) v.x = x; else v.y = x;
+    }
+    *reinterpret_cast<double2*>(Linv + (long long)i * PB + c) = v;
   }
   // sum of log L_ii in a fixed order
   double lg = (tid < w) ? log(G[tid * GLD + tid]) : 0.0;
