@@ -173,6 +173,9 @@ void smnngp_set_tile_variant(int v);
  * high-priority side stream while the bulk of the trailing update runs (fork / join with events: still
  * enqueue-only and graph-capturable); 0 = single stream */
 void smnngp_set_lookahead(int on);
+/* diagnostic: device buffer (>= 64 int64) receiving clock64() at the phase boundaries of the diagonal-block
+ * kernel; NULL switches it off */
+void smnngp_debug_potf2_clocks(long long* dev_buf);
 /* resident CTAs per SM of the update kernel for a tile variant (diagnostic) */
 int smnngp_debug_occupancy(int variant);
 

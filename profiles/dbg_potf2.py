@@ -16,3 +16,19 @@ for w in (32, 64, 96, 128):
     for _ in range(200): be.factor_diag(a, linv, ld, info, 0)
     e1.record(); e1.synchronize()
     print(f"potf2 w={w}: {e0.elapsed_time(e1) / 200 * 1e3:.1f} us per call", flush=True)
+
+import ctypes as C
+lib = sm._lib.load()
+clk = torch.zeros(64, dtype=torch.int64, device="cuda")
+lib.smnngp_debug_potf2_clocks(C.c_void_p(clk.data_ptr()))
+w = 128
+b = rng.standard_normal((w, w + 8)); a = torch.from_numpy(b @ b.T / (w + 8) + 1e-3 * np.eye(w)).cuda()
+for _ in range(3):
+    be.factor_diag(a, linv, ld, info, 0); torch.cuda.synchronize()
+t = clk.cpu().numpy()
+lib.smnngp_debug_potf2_clocks(C.c_void_p(0))
+d = np.diff(t[: 2 + 3 * (128 // 16) + 2])
+names = ["stage"] + sum([[f"diag{b}", f"panel{b}", f"update{b}"] for b in range(128 // 16)], []) + ["inv-assembly", "write-back"]
+tot = d.sum()
+print("potf2 phases (cycles):", {n: int(v) for n, v in zip(names, d)})
+print("total cycles", int(tot), "diag sum", int(d[1::3][:8].sum()), "panel sum", int(d[2::3][:8].sum()), "update sum", int(d[3::3][:8].sum()))

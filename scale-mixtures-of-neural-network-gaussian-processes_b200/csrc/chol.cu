@@ -186,12 +186,27 @@ constexpr int PF_SMEM_BYTES = (PB * GLD + NBLK * DB * MLD + 64) * 8;
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
+// 1/sqrt(d) without the library's special-case branches: MUFU.RSQ64H seed + two coupled Newton steps + one
+// correction (<= 1 ulp for normal d > 0).  The library rsqrt() / division cost ~300 dependent cycles each and
+// sat on the critical path of every pivot: they were 60 % of the whole diagonal-block kernel.
+__device__ __forceinline__ double rsqrt_fast(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double g = d * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  h = fma(h, r, h);                       // h ~ 0.5 / sqrt(d)
+  double y2 = h + h;
+  return fma(y2, fma(-d * y2, y2, 1.0) * 0.5, y2);   // one more Newton step on y = 1/sqrt(d)
+}
+
 // warp 0, lane = row (lanes >= DB idle along): factor the DB x DB block at Gbb (lower part valid), write L back
 // (lower) and inv(L) to M.
 __device__ __forceinline__ void diag_factor_invert(double* __restrict__ Gbb, double* __restrict__ M, int lane,
                                                    int col_base, int& bad) {
   const int row = lane < DB ? lane : DB - 1;
-  double a[DB];
+  double a[DB], rinvs[DB];
 #pragma unroll
   for (int c = 0; c < DB; c++) a[c] = Gbb[row * GLD + c];
 #pragma unroll
@@ -201,7 +216,8 @@ __device__ __forceinline__ void diag_factor_invert(double* __restrict__ Gbb, dou
       if (bad == 0) bad = col_base + j + 1;
       d = __longlong_as_double(0x7ff8000000000000ll);
     }
-    const double rinv = rsqrt(d);
+    const double rinv = rsqrt_fast(d);
+    rinvs[j] = rinv;                                          // = 1 / L_jj (same value in every lane)
     const double l = (lane == j) ? d * rinv : a[j] * rinv;   // lane j: L_jj = sqrt(d); lanes > j: L_ij
     a[j] = l;
 #pragma unroll
@@ -213,7 +229,7 @@ __device__ __forceinline__ void diag_factor_invert(double* __restrict__ Gbb, dou
       if (c <= lane) Gbb[lane * GLD + c] = a[c];
   }
   __syncwarp();
-  // inverse, lane = column c: x_i = (delta_ic - sum_{k=c}^{i-1} L_ik x_k) / L_ii   (L_ik: broadcast reads)
+  // inverse, lane = column c: x_i = (delta_ic - sum_{k=c}^{i-1} L_ik x_k) * (1 / L_ii)   (L_ik: broadcast reads)
   double x[DB];
 #pragma unroll
   for (int i = 0; i < DB; i++) {
@@ -223,7 +239,7 @@ __device__ __forceinline__ void diag_factor_invert(double* __restrict__ Gbb, dou
       s0 = fma(-Gbb[i * GLD + k], x[k], s0);
       if (k + 1 < i) s1 = fma(-Gbb[i * GLD + k + 1], x[k + 1], s1);
     }
-    const double v = (s0 + s1) / Gbb[i * GLD + i];
+    const double v = (s0 + s1) * rinvs[i];
     x[i] = (i >= lane) ? v : 0.0;     // rows above the column's diagonal stay exactly zero
   }
   if (lane < DB) {
@@ -243,7 +259,10 @@ __device__ __forceinline__ void tile_nn(double (&acc)[2], const double* __restri
 
 __global__ void __launch_bounds__(PF_THREADS, 1)
 potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restrict__ Linv,
-                   double* __restrict__ logdet, int* __restrict__ info, int gcol0) {
+                   double* __restrict__ logdet, int* __restrict__ info, int gcol0, long long* __restrict__ clk) {
+  int nclk = 0;
+#define PF_CLK() do { if (clk != nullptr && threadIdx.x == 0) clk[nclk++] = clock64(); } while (0)
+  PF_CLK();
   extern __shared__ __align__(16) double sm[];
   double* G = sm;                          // [128][132]
   double* Mi = G + PB * GLD;               // NBLK x [DB][MLD] inverse diagonal blocks
@@ -252,29 +271,43 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
   const int nblk = (w + DB - 1) / DB;
   const int wp = nblk * DB;                // padded size (identity padding)
 
-  // stage the lower triangle (the upper part of G is scratch for the inverse assembly and must start at zero)
-  for (int idx = tid; idx < wp * (PB / 2); idx += PF_THREADS) {
-    const int i = idx >> 6, c = (idx & 63) * 2;
-    double2 g = make_double2(0.0, 0.0);
-    if (i < w && c <= i) {
-      const double* src = A + (long long)i * lda + c;
-      g.x = src[0];
-      if (c + 1 <= i) g.y = src[1];
+  // stage the lower triangle (the upper part of G is scratch for the inverse assembly and must start at zero);
+  // 8 independent 16-byte slots per thread and batch so the global loads overlap
+  for (int base = 0; base < wp * (PB / 2); base += PF_THREADS * 8) {
+    double2 g[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int idx = base + u * PF_THREADS + tid;
+      const int i = idx >> 6, c = (idx & 63) * 2;
+      g[u] = make_double2(0.0, 0.0);
+      if (idx < wp * (PB / 2) && i < w && c <= i) {
+        const double* src = A + (long long)i * lda + c;
+        g[u].x = src[0];
+        if (c + 1 <= i) g[u].y = src[1];
+      }
     }
-    if (i >= w) {
-      if (c == i) g.x = 1.0;
-      if (c + 1 == i) g.y = 1.0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int idx = base + u * PF_THREADS + tid;
+      if (idx >= wp * (PB / 2)) continue;
+      const int i = idx >> 6, c = (idx & 63) * 2;
+      if (i >= w) {
+        if (c == i) g[u].x = 1.0;
+        if (c + 1 == i) g[u].y = 1.0;
+      }
+      G[i * GLD + c] = g[u].x;
+      G[i * GLD + c + 1] = g[u].y;
     }
-    G[i * GLD + c] = g.x;
-    G[i * GLD + c + 1] = g.y;
   }
   __syncthreads();
+  PF_CLK();   // 1: staged
 
   int bad = 0;
   for (int b = 0; b < nblk; b++) {
     const int b0 = b * DB;
     if (warp == 0) diag_factor_invert(G + b0 * GLD + b0, Mi + b * DB * MLD, lane, b0, bad);
     __syncthreads();
+    PF_CLK();   // diag
     const int r_first = b0 + DB;
     const int nstrips = (wp - r_first) / 8;
     // panel: rows below, P = S_ib * inv(L_bb)^T   (a warp owns whole 8-row strips -> in place)
@@ -299,6 +332,7 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
       for (int nt = 0; nt < NT; nt++) { op[nt * 8] = acc[nt][0]; op[nt * 8 + 1] = acc[nt][1]; }
     }
     __syncthreads();
+    PF_CLK();   // panel
     // trailing update: S_ic -= P_i P_c^T for r_first <= c-tile <= row strip
     for (int s = warp; s < nstrips; s += PF_WARPS) {
       const int r0 = r_first + s * 8;
@@ -317,6 +351,7 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
       }
     }
     __syncthreads();
+    PF_CLK();   // update
   }
 
   // ---- inverse assembly: X_ik (i > k) is kept at block position (k, i) of G (upper triangle, untransposed)
@@ -364,11 +399,14 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
     }
     __syncthreads();
   }
+  PF_CLK();   // inverse assembled
 
-  // write back: L (lower part only) and inv(L) (full 128 x 128: zero above the diagonal, identity padded)
-  for (int idx = tid; idx < PB * (PB / 2); idx += PF_THREADS) {
+  // write back: L and inv(L), lower parts only (the strict upper triangle of A is never touched; the part of
+  // the inverse above the diagonal is zero and the workspace block was zero-filled when the factorisation began)
+  for (int idx = tid; idx < wp * (PB / 2); idx += PF_THREADS) {
     const int i = idx >> 6, c = (idx & 63) * 2;
-    if (i < w && c <= i) {
+    if (c > i) continue;
+    if (i < w) {
       double* dst = A + (long long)i * lda + c;
       dst[0] = G[i * GLD + c];
       if (c + 1 <= i) dst[1] = G[i * GLD + c + 1];
@@ -378,12 +416,10 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
     for (int e = 0; e < 2; e++) {
       const int cc = c + e;
       double x = 0.0;
-      if (i < wp && cc <= i) {
+      if (cc <= i) {
         const int bi = i / DB, bc = cc / DB;
         x = (bi == bc) ? Mi[bi * DB * MLD + (i - bi * DB) * MLD + (cc - bc * DB)]
                        : G[(bc * DB + (i - bi * DB)) * GLD + bi * DB + (cc - bc * DB)];
-      } else if (i == cc) {
-        x = 1.0;
       }
       if (e == 0) v.x = x; else v.y = x;
     }
@@ -398,9 +434,11 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
   if (tid == 0) {
     double s = 0.0;
     for (int k = 0; k < PB / 32; k++) s += red[k];
-    *logdet += s;
-    if (bad != 0 && *info == 0) *info = gcol0 + bad;
+    atomicAdd(logdet, s);                       // kernels on one stream: still a fixed order, no load latency
+    if (bad != 0) atomicCAS(info, 0, gcol0 + bad);
   }
+  PF_CLK();   // written back
+#undef PF_CLK
 }
 
 }  // namespace
@@ -424,12 +462,17 @@ int debug_gemm_occupancy(int variant) {
 cudaError_t launch_gemm_store(cudaStream_t s, const GemmParams& p) { return launch_gemm_t<EPI_STORE>(s, p); }
 cudaError_t launch_gemm_sub(cudaStream_t s, const GemmParams& p) { return launch_gemm_t<EPI_SUB>(s, p); }
 
+long long*& potf2_clock_buffer() {
+  static long long* p = nullptr;
+  return p;
+}
+
 cudaError_t launch_potf2_trtri(cudaStream_t s, double* A, long long lda, int w, double* Linv, double* logdet,
                                int* info, int global_col0) {
   cudaError_t e = cudaFuncSetAttribute(potf2_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        PF_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  potf2_trtri_kernel<<<1, PF_THREADS, PF_SMEM_BYTES, s>>>(A, lda, w, Linv, logdet, info, global_col0);
+  potf2_trtri_kernel<<<1, PF_THREADS, PF_SMEM_BYTES, s>>>(A, lda, w, Linv, logdet, info, global_col0, potf2_clock_buffer());
   instr().launches++;
   return cudaGetLastError();
 }
@@ -437,8 +480,14 @@ cudaError_t launch_potf2_trtri(cudaStream_t s, double* A, long long lda, int w, 
 // Plain right-looking two-level factorisation on ONE stream (also the building block of the look-ahead variant,
 // where it factors the NB x NB diagonal blocks).
 static cudaError_t potrf_serial(cudaStream_t s, double* A, long long lda, long long Mtot, long long N, int NB,
-                                double* Linv_base, double* logdet, int* info, long long linv_stride, int gcol_base) {
+                                double* Linv_base, double* logdet, int* info, long long linv_stride, int gcol_base,
+                                bool zero_linv = true) {
   cudaError_t e;
+  if (zero_linv) {     // the diagonal kernel only writes the lower part of each inverse block
+    const long long blocks = linv_stride == 0 ? 1 : (N + PB - 1) / PB;
+    e = cudaMemsetAsync(Linv_base, 0, (size_t)blocks * PB * PB * sizeof(double), s);
+    if (e != cudaSuccess) return e;
+  }
   for (long long c0 = 0; c0 < N; c0 += NB) {
     const long long c1 = (c0 + NB < N) ? c0 + NB : N;
     for (long long j0 = c0; j0 < c1; j0 += PB) {
@@ -542,7 +591,7 @@ cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long 
     const long long c1 = (c0 + NB < N) ? c0 + NB : N;
     const int w = (int)(c1 - c0);
     // side: diagonal block (w x w) with its block inverses
-    LA_CK(potrf_serial(la->side, A + c0 * lda + c0, lda, w, w, NB, Linv_base, logdet, info, ls, (int)c0));
+    LA_CK(potrf_serial(la->side, A + c0 * lda + c0, lda, w, w, NB, Linv_base, logdet, info, ls, (int)c0, c0 == 0));
     LA_CK(cudaEventRecord(la->ev_diag, la->side));
     LA_CK(cudaStreamWaitEvent(s, la->ev_diag, 0));
     // main: rows below the diagonal block <- rows * L_pp^-T by 128-block substitution
