@@ -27,7 +27,7 @@ __all__ = [
     "softplus", "softplus_inverse", "nngp_gram", "nngp_diag", "jitter", "multivariate_t_logpdf",
     "multivariate_normal_logpdf", "prior_logpdf", "spr_loss", "nt_predict", "student_t_logpdf",
     "normal_logpdf", "likelihood_logpdf", "spr_test_nll", "sample_f_iid_moments", "test_log_likelihood",
-    "get_correct_count",
+    "get_correct_count", "nngp_gram_dual", "spr_loss_grad",
 ]
 
 ACTS = ("relu", "erf")
@@ -215,6 +215,119 @@ def spr_loss(x, y, *, num_hiddens, act="relu", w_std=1.0, b_std=0.0, last_w_std=
                     arch=arch, fast=fast)
     cov[np.diag_indices(n)] += eps                                  # == + jitter(n, eps) without the N x N eye
     return -prior_logpdf(y, cov, kind=kind, a=a, b=b) / n
+
+
+# ----------------------------------------------------------------------------------------------------------
+# gradient of SPR.loss w.r.t. the six positive scalars - what objax.GradValues(model.loss, vars) computes in the
+# training loop (experiments/regression/train.py:62-66, :178-179) by reverse-mode AD through the same path.
+# Restated analytically: forward-mode duals of the layer recursion + d log p / d Sigma in closed form.
+# ----------------------------------------------------------------------------------------------------------
+def _act_diag_dual(q, act):
+    """(phi(q), dphi/dq) on the diagonal."""
+    if act == "relu":
+        return 0.5 * q, np.full_like(q, 0.5)
+    return ((2.0 / math.pi) * np.arcsin(2.0 * q / (1.0 + 2.0 * q)),
+            (4.0 / math.pi) / ((1.0 + 2.0 * q) * np.sqrt(1.0 + 4.0 * q)))
+
+
+def _act_offdiag_dual(k, q1, q2, act):
+    """(phi, dphi/dk, dphi/dq1, dphi/dq2), all [N,M], for one nonlinearity."""
+    if act == "relu":
+        prod = q1[:, None] * q2[None, :]
+        s = np.sqrt(np.maximum(prod - k * k, 0.0))
+        theta = np.where((s == 0.0) & (k == 0.0), math.pi / 2, np.arctan2(s, k))
+        phi = s / (2.0 * math.pi) + (0.5 - theta / (2.0 * math.pi)) * k
+        with np.errstate(divide="ignore", invalid="ignore"):
+            i1 = np.where(q1 > 0.0, 1.0 / (4.0 * math.pi * q1), 0.0)
+            i2 = np.where(q2 > 0.0, 1.0 / (4.0 * math.pi * q2), 0.0)
+        return phi, 0.5 - theta / (2.0 * math.pi), s * i1[:, None], s * i2[None, :]
+    t1, t2 = 1.0 / np.sqrt(1.0 + 2.0 * q1), 1.0 / np.sqrt(1.0 + 2.0 * q2)
+    x = 2.0 * k * t1[:, None] * t2[None, :]
+    g = (2.0 / math.pi) / np.sqrt(np.maximum(1.0 - x * x, 1e-300))
+    phi = (2.0 / math.pi) * np.arcsin(np.clip(x, -1.0, 1.0))
+    # d t / d q = -t^3
+    return (phi, g * 2.0 * t1[:, None] * t2[None, :], g * (-x) * (t1 * t1)[:, None], g * (-x) * (t2 * t2)[None, :])
+
+
+def nngp_gram_dual(x1, x2=None, *, num_hiddens, act="relu", w_std=1.0, b_std=0.0, last_w_std=1.0, arch="mlp"):
+    """K and its partial derivatives w.r.t. (w_std, b_std, last_w_std): returns (K, dK_w, dK_b, dK_v)."""
+    if act not in ACTS:
+        raise KeyError("Unsupported act '{}'".format(act))
+    if arch not in ARCHS:
+        raise ValueError(f"Unsupported network '{arch}'")
+    x1 = np.ascontiguousarray(x1, dtype=np.float64)
+    x2 = x1 if x2 is None else np.ascontiguousarray(x2, dtype=np.float64)
+    d = x1.shape[1]
+    w2, b2, v2 = w_std * w_std, b_std * b_std, last_w_std * last_w_std
+
+    # state: value + (d/dw, d/db) for k [N,M], q1 [N], q2 [M]
+    k = (x1 @ x2.T) / d
+    q1 = np.einsum("ij,ij->i", x1, x1) / d
+    q2 = np.einsum("ij,ij->i", x2, x2) / d
+    zk, z1, z2 = np.zeros_like(k), np.zeros_like(q1), np.zeros_like(q2)
+    K, Q1, Q2 = (k, zk, zk), (q1, z1, z1), (q2, z2, z2)
+
+    def dense(t):
+        v, dw, db = t
+        return (w2 * v + b2, 2.0 * w_std * v + w2 * dw, w2 * db + 2.0 * b_std)
+
+    def act_k(K, Q1, Q2):
+        phi, pk, p1, p2 = _act_offdiag_dual(K[0], Q1[0], Q2[0], act)
+        return (phi,) + tuple(pk * K[i] + p1 * Q1[i][:, None] + p2 * Q2[i][None, :] for i in (1, 2))
+
+    def act_q(Q):
+        phi, pq = _act_diag_dual(Q[0], act)
+        return (phi, pq * Q[1], pq * Q[2])
+
+    def add(a, b):
+        return tuple(u + v for u, v in zip(a, b))
+
+    if arch == "mlp":
+        for _ in range(num_hiddens):
+            K, Q1, Q2 = dense(K), dense(Q1), dense(Q2)
+            K, Q1, Q2 = act_k(K, Q1, Q2), act_q(Q1), act_q(Q2)
+    else:
+        K, Q1, Q2 = dense(K), dense(Q1), dense(Q2)
+        for _ in range(num_hiddens):
+            K, Q1, Q2 = add(K, dense(act_k(K, Q1, Q2))), add(Q1, dense(act_q(Q1))), add(Q2, dense(act_q(Q2)))
+        K = act_k(K, Q1, Q2)
+    return v2 * K[0], v2 * K[1], v2 * K[2], 2.0 * last_w_std * K[0]
+
+
+def spr_loss_grad(x, y, *, num_hiddens, act="relu", w_std=1.0, b_std=0.0, last_w_std=1.0, arch="mlp", eps=1e-6,
+                  kind="student_t", a=2.0, b=2.0):
+    """(loss, grad) with grad = d loss / d (w_std, b_std, last_w_std, eps, alpha, beta), loss = SPR.loss
+    (spax/models.py:93-98).  With A = K + eps I, alpha_v = A^-1 y, quad = y^T A^-1 y:
+        d log p / d A = 1/2 (gamma alpha_v alpha_v^T - A^-1),  gamma = (2a + N) / ((2a + a quad / b) b / a)  [t],  1 [gauss]
+    and the (a, b) dependence of the Student-t density in closed form (quad / nu = quad / (2b) does not depend on a)."""
+    from scipy.special import digamma
+    n = x.shape[0]
+    K, dKw, dKb, dKv = nngp_gram_dual(x, num_hiddens=num_hiddens, act=act, w_std=w_std, b_std=b_std,
+                                      last_w_std=last_w_std, arch=arch)
+    A = K + eps * np.eye(n)
+    try:
+        c = sla.cho_factor(A, lower=True, check_finite=False)
+    except sla.LinAlgError:
+        return float("nan"), np.full(6, np.nan)
+    Ainv = sla.cho_solve(c, np.eye(n), check_finite=False)
+    al = Ainv @ y
+    quad = float(y @ al)
+    logdet_half = float(np.log(np.diag(c[0])).sum())
+    if kind == "student_t":
+        nu, t = 2.0 * a, a + 0.5 * n
+        logp = (-t * np.log1p(quad / (2.0 * b)) - 0.5 * n * np.log(nu * np.pi) + gammaln(t) - gammaln(a)
+                - 0.5 * n * np.log(b / a) - logdet_half)
+        gamma = (nu + n) / ((nu + quad * a / b) * (b / a))
+        dlp_da = -np.log1p(quad / (2.0 * b)) + digamma(t) - digamma(a)
+        dlp_db = t * quad / (b * (2.0 * b + quad)) - 0.5 * n / b
+    elif kind == "gauss":
+        logp = -0.5 * quad - 0.5 * n * np.log(2 * np.pi) - logdet_half
+        gamma, dlp_da, dlp_db = 1.0, 0.0, 0.0
+    else:
+        raise KeyError(kind)
+    G = 0.5 * (gamma * np.outer(al, al) - Ainv)
+    dlp = np.array([np.sum(G * dKw), np.sum(G * dKb), np.sum(G * dKv), np.trace(G), dlp_da, dlp_db])
+    return float(-logp / n), -dlp / n
 
 
 # ----------------------------------------------------------------------------------------------------------

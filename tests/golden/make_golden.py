@@ -60,6 +60,22 @@ def chol_solve_stats(S, y):
     return sum(mp.log(L[i, i]) for i in range(S.rows)), sum(z[i] ** 2 for i in range(S.rows)), L
 
 
+def loss_mp(X, ymp, L, act, arch, w, bs, v, eps, a, b, kind):
+    """SPR.loss (spax/models.py:93-98) entirely in mp; every scalar argument may be an mpf (differentiated below)."""
+    n = len(X)
+    K = gram(X, X, L, act, arch, w, bs, v)
+    S = K + eps * mp.eye(n)
+    if kind == "t":
+        ld, zz, _ = chol_solve_stats((b / a) * S, ymp)
+        df = 2 * a
+        tt = (df + n) / 2
+        lml = -tt * mp.log(1 + zz / df) - mp.mpf(n) / 2 * mp.log(df * PI) + mp.loggamma(tt) - mp.loggamma(df / 2) - ld
+    else:
+        ld, zz, _ = chol_solve_stats(S, ymp)
+        lml = -zz / 2 - mp.mpf(n) / 2 * mp.log(2 * PI) - ld
+    return -lml / n
+
+
 def to_np(m):
     return np.array([[float(m[i, j]) for j in range(m.cols)] for i in range(m.rows)], dtype=np.float64)
 
@@ -96,6 +112,18 @@ def main():
         ld, zz, _ = chol_solve_stats(S, ymp)
         lml_g = -zz / 2 - mp.mpf(n) / 2 * mp.log(2 * PI) - ld
         out[f"loss_t{vi}"], out[f"loss_g{vi}"] = float(-lml_t / n), float(-lml_g / n)
+        # --- d loss / d (w_std, b_std, last_w_std, eps, alpha, beta): what objax.GradValues(model.loss, vars)
+        #     yields before the softplus chain rule (regression/train.py:62-66); 50-digit central differences
+        base = [mp.mpf(w), mp.mpf(bs), mp.mpf(v), mp.mpf(eps), mp.mpf(a), mp.mpf(b)]
+        for key in ("t", "g"):
+            g = []
+            for pi in range(6):
+                def f(z, pi=pi, key=key):
+                    q = list(base)
+                    q[pi] = z
+                    return loss_mp(X, ymp, L, act, arch, *q, key)
+                g.append(float(mp.diff(f, base[pi])))
+            out[f"grad_{key}{vi}"] = np.array(g)
         # --- predict (relative regulariser) + test_nll
         tr = sum(K[i, i] for i in range(n)) / n
         A1 = K + mp.mpf(eps) * tr * mp.eye(n)

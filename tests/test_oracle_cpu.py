@@ -39,6 +39,34 @@ def test_oracle_matches_mpmath_golden(vi, kw):
         assert abs(nll - float(GOLD[f"nll_{key}{vi}"])) <= 1e-9 * abs(nll)
 
 
+@pytest.mark.parametrize("vi,kw", list(_variants()))
+def test_oracle_gradient_matches_mpmath_golden(vi, kw):
+    """d SPR.loss / d (w_std, b_std, last_w_std, eps, alpha, beta) against 50-digit mp differentiation."""
+    x, y = GOLD["x"], GOLD["y"]
+    eps, a, b = float(GOLD["eps"]), float(GOLD["a"]), float(GOLD["b"])
+    for kind, key in (("student_t", "t"), ("gauss", "g")):
+        loss, grad = orc.spr_loss_grad(x, y, eps=eps, kind=kind, a=a, b=b, **kw)
+        assert abs(loss - float(GOLD[f"loss_{key}{vi}"])) <= 1e-11 * abs(loss)
+        ref = GOLD[f"grad_{key}{vi}"]
+        # eps = 1e-3 on a matrix with a collinear pair: cond ~ 1e4, so ~1e-11 relative on the explicit inverse
+        assert np.abs(grad - ref).max() <= 1e-9 * np.abs(ref).max(), (grad, ref)
+
+
+def test_oracle_gram_dual_matches_finite_differences():
+    rng = np.random.default_rng(5)
+    x, x2 = rng.standard_normal((40, 6)), rng.standard_normal((17, 6))
+    for _, kw in _variants():
+        K, dw, db, dv = orc.nngp_gram_dual(x, x2, **kw)
+        assert np.abs(K - orc.nngp_gram(x, x2, **kw)).max() <= 1e-14 * np.abs(K).max()
+        for name, d in (("w_std", dw), ("b_std", db), ("last_w_std", dv)):
+            h = 1e-6
+            p, m = dict(kw), dict(kw)
+            p[name] += h
+            m[name] -= h
+            fd = (orc.nngp_gram(x, x2, **p) - orc.nngp_gram(x, x2, **m)) / (2 * h)
+            assert np.abs(fd - d).max() <= 1e-8 * max(np.abs(d).max(), 1.0), name
+
+
 def test_c_recursion_matches_numpy():
     rng = np.random.default_rng(0)
     x, x2 = rng.standard_normal((300, 7)), rng.standard_normal((111, 7))
