@@ -83,6 +83,18 @@ int smnngp_lml_f64(void* stream, const double* X, const double* y, int64_t N, in
                    int arch, const double* hp_dev, int kind, void* workspace, size_t workspace_bytes,
                    double* out_dev, int* info_dev);
 
+/* ---- loss AND its gradient w.r.t. the six scalars: what objax.GradValues(model.loss, model.vars()) evaluates at
+ * every step of the reference's training loop (experiments/regression/train.py:62-66, :178-179) by reverse-mode
+ * AD through spax/models.py:93-98.  out_dev[4] as smnngp_lml_f64; grad_dev[6] = d loss / d {w_std, b_std,
+ * last_w_std, eps, alpha, beta} (loss = -log p / N; derivatives w.r.t. the constrained "safe" values - the caller
+ * applies the softplus chain rule, spax/bijectors.py:51-53).  A^-1 is formed explicitly from the factor (identity
+ * rows carried through the factorisation, one SYRK) and dK/dtheta is contracted inside a second Gram pass in dual
+ * arithmetic; ~3x the work of the value alone, workspace 16 N^2 bytes.  Bit-reproducible. */
+size_t smnngp_lml_grad_workspace_bytes(int64_t N, int64_t D, int n_hidden, int arch);
+int smnngp_lml_grad_f64(void* stream, const double* X, const double* y, int64_t N, int64_t D, int n_hidden, int act,
+                        int arch, const double* hp_dev, int kind, void* workspace, size_t workspace_bytes,
+                        double* out_dev, double* grad_dev, int* info_dev);
+
 /* ---- predictive: replaces NNGPKernel.predict (spax/kernels.py:29-32 -> neural_tangents
  * gradient_descent_mse_ensemble, get="nngp", compute_cov=True) with `shift` = EPS_REL.  Y is [N, C];
  * mean_out [T, C]; var_out [T] = diag(cov) - the only part of cov the reference consumes
@@ -155,6 +167,8 @@ int smnngp_stage_lml_finalize_f64(void* stream, const double* sums_dev, const do
  * outputs are HOST pointers; device staging comes from a grow-only arena released by smnngp_host_release(). */
 int smnngp_lml_host_f64(const double* X, const double* y, int64_t N, int64_t D, int n_hidden, int act, int arch,
                         const double* hp, int kind, double* out, int* info);
+int smnngp_lml_grad_host_f64(const double* X, const double* y, int64_t N, int64_t D, int n_hidden, int act, int arch,
+                             const double* hp, int kind, double* out, double* grad, int* info);
 int smnngp_predict_host_f64(const double* X, const double* Y, const double* Xt, int64_t N, int64_t T, int64_t C,
                             int64_t D, int n_hidden, int act, int arch, const double* hp, int shift,
                             double* mean_out, double* var_out, int* info);

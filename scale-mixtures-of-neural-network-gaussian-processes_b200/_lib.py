@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsmnngp.so")
-SOURCES = ["gram.cu", "chol.cu", "reduce.cu", "api.cu", "stages.cu", "draws.cu"]
+SOURCES = ["gram.cu", "chol.cu", "reduce.cu", "api.cu", "stages.cu", "draws.cu", "grad.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets"]
 
@@ -22,7 +22,8 @@ EXPORTS = [
     "smnngp_abi_version", "smnngp_last_error", "smnngp_gram_workspace_bytes", "smnngp_gram_f64",
     "smnngp_nngp_diag_f64", "smnngp_potrf_workspace_bytes", "smnngp_potrf_f64", "smnngp_potrf_trapezoid_f64",
     "smnngp_cov_solve_workspace_bytes", "smnngp_cov_solve_f64",
-    "smnngp_lml_workspace_bytes", "smnngp_lml_f64", "smnngp_predict_workspace_bytes", "smnngp_predict_f64", "smnngp_predict_cov_f64",
+    "smnngp_lml_workspace_bytes", "smnngp_lml_f64", "smnngp_lml_grad_workspace_bytes", "smnngp_lml_grad_f64",
+    "smnngp_lml_grad_host_f64", "smnngp_predict_workspace_bytes", "smnngp_predict_f64", "smnngp_predict_cov_f64",
     "smnngp_test_nll_f64", "smnngp_lml_host_f64", "smnngp_predict_host_f64", "smnngp_test_nll_host_f64",
     "smnngp_host_release", "smnngp_set_panel_width", "smnngp_set_tile_variant", "smnngp_debug_occupancy", "smnngp_set_lookahead", "smnngp_debug_potf2_clocks",
     "smnngp_sample_f_iid_f64", "smnngp_draw_metrics_f64",
@@ -98,6 +99,10 @@ def _declare(lib):
     lib.smnngp_lml_workspace_bytes.restype = _sz
     lib.smnngp_lml_workspace_bytes.argtypes = [_i64, _i64, _i, _i]
     lib.smnngp_lml_f64.argtypes = [_vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _i, _vp, _sz, _vp, _vp]
+    lib.smnngp_lml_grad_workspace_bytes.restype = _sz
+    lib.smnngp_lml_grad_workspace_bytes.argtypes = [_i64, _i64, _i, _i]
+    lib.smnngp_lml_grad_f64.argtypes = [_vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _i, _vp, _sz, _vp, _vp, _vp]
+    lib.smnngp_lml_grad_host_f64.argtypes = [_vp, _vp, _i64, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp]
     lib.smnngp_predict_workspace_bytes.restype = _sz
     lib.smnngp_predict_workspace_bytes.argtypes = [_i64, _i64, _i64, _i64, _i, _i]
     lib.smnngp_predict_f64.argtypes = [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i, _i, _i, _vp, _i, _vp, _sz,

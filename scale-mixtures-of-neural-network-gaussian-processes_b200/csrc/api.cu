@@ -337,6 +337,78 @@ int smnngp_lml_f64(void* stream, const double* X, const double* y, int64_t N, in
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// loss and its gradient w.r.t. the six scalars
+namespace {
+struct GradWs {
+  double *scal, *tab, *q, *tab3, *linv, *alpha, *partial, *A;
+  long long lda, slots;
+};
+size_t carve_grad(Carver& c, GradWs& w, long long N, int n_act) {
+  const size_t na = (size_t)(n_act > 0 ? n_act : 1);
+  w.scal = c.take<double>(SC_COUNT);
+  w.tab = c.take<double>(na * N);
+  w.q = c.take<double>(N);
+  w.tab3 = c.take<double>(3 * na * N);
+  w.linv = c.take<double>(LINV_BLOCKS * PB * PB);
+  w.alpha = c.take<double>(N);
+  w.slots = grad_partial_slots(N);
+  w.partial = c.take<double>((size_t)w.slots * 4);
+  w.lda = round_up(N, 16);
+  w.A = c.take<double>((size_t)(2 * N + 1) * w.lda);   // K -> L -> A^-1 | y^T -> z^T | I -> U = L^-T
+  return c.total();
+}
+}  // namespace
+
+size_t smnngp_lml_grad_workspace_bytes(int64_t N, int64_t D, int n_hidden, int arch) {
+  (void)D;
+  Carver c(nullptr);
+  GradWs w;
+  return carve_grad(c, w, N, n_act_applications(n_hidden, arch));
+}
+
+int smnngp_lml_grad_f64(void* stream, const double* X, const double* y, int64_t N, int64_t D, int n_hidden, int act,
+                        int arch, const double* hp_dev, int kind, void* workspace, size_t workspace_bytes,
+                        double* out_dev, double* grad_dev, int* info_dev) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!X || !y || !hp_dev || !out_dev || !grad_dev || !info_dev || N <= 0 || D <= 0 ||
+      !valid_stack(n_hidden, act, arch) || (kind != KIND_GAUSS && kind != KIND_STUDENT_T) ||
+      2 * N + 1 > INT32_MAX || D > INT32_MAX)
+    return fail(SMNNGP_EINVAL, "smnngp_lml_grad_f64: invalid argument");
+  const int n_act = n_act_applications(n_hidden, arch);
+  Carver c(workspace);
+  GradWs w;
+  if (carve_grad(c, w, N, n_act) > workspace_bytes || !workspace)
+    return fail(SMNNGP_EWORKSPACE, "smnngp_lml_grad_f64: workspace too small");
+  double* zrow = w.A + N * w.lda;
+  double* U = w.A + (N + 1) * w.lda;
+  CU(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
+  CU(launch_qtable(s, X, D, (int)N, (int)D, n_hidden, act, arch, hp_dev, w.tab, N, w.q));
+  CU(launch_scalars(s, w.q, (int)N, hp_dev, w.scal));
+  CU(launch_qtable_dual(s, X, D, (int)N, (int)D, n_hidden, act, arch, hp_dev, w.tab3, N));
+  CU(enqueue_sym_gram(s, X, N, D, n_hidden, act, arch, hp_dev, w.tab, w.scal, SHIFT_EPS_ABS, 0, w.A, w.lda));
+  CU(cudaMemcpyAsync(zrow, y, N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  CU(launch_set_identity(s, U, w.lda, N));
+  // forward value exactly as smnngp_lml_f64; the identity rows come out as U = L^-T
+  CU(potrf_trapezoid(s, w.A, w.lda, 2 * N + 1, N, pick_nb(N), w.linv, w.scal + SC_LOGDET, info_dev, 0, N + 1));
+  CU(launch_sumsq(s, zrow, N, w.scal + SC_QUAD));
+  CU(launch_lml_finalize(s, w.scal, hp_dev, kind, N, info_dev, out_dev));
+  // a = A^-1 y = U z;  A^-1 = U U^T over the (now free) lower triangle of the factor
+  CU(launch_upper_gemv(s, U, w.lda, zrow, N, w.alpha));
+  {
+    GemmParams g{};
+    g.A = U; g.lda = w.lda;
+    g.B = U; g.ldb = w.lda;
+    g.C = w.A; g.ldc = w.lda;
+    g.M = (int)N; g.N = (int)N; g.K = (int)N; g.lower = 1; g.k_from_row = 1;
+    CU(launch_gemm_store_lower(s, g));
+  }
+  CU(launch_grad_gram(s, X, N, D, n_hidden, act, arch, hp_dev, w.tab3, N, w.A, w.lda, w.alpha, w.scal + SC_QUAD,
+                      kind, w.partial, w.slots));
+  CU(launch_grad_finalize(s, w.partial, w.slots, hp_dev, w.scal + SC_QUAD, kind, N, info_dev, grad_dev));
+  return SMNNGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 size_t smnngp_predict_workspace_bytes(int64_t N, int64_t T, int64_t C, int64_t D, int n_hidden, int arch) {
   (void)D;
   Carver c(nullptr);
@@ -484,6 +556,40 @@ int smnngp_lml_host_f64(const double* X, const double* y, int64_t N, int64_t D, 
   if (rc != SMNNGP_OK) return rc;
   int hinfo = 0;
   CU(cudaMemcpyAsync(out, dout, 4 * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (info) *info = hinfo;
+  return SMNNGP_OK;
+}
+
+int smnngp_lml_grad_host_f64(const double* X, const double* y, int64_t N, int64_t D, int n_hidden, int act, int arch,
+                             const double* hp, int kind, double* out, double* grad, int* info) {
+  if (!X || !y || !hp || !out || !grad || N <= 0 || D <= 0)
+    return fail(SMNNGP_EINVAL, "smnngp_lml_grad_host_f64: invalid argument");
+  const size_t ws_bytes = smnngp_lml_grad_workspace_bytes(N, D, n_hidden, arch);
+  Carver c(nullptr);
+  c.take<double>((size_t)N * D); c.take<double>(N); c.take<double>(HP_COUNT); c.take<double>(4);
+  c.take<double>(HP_COUNT); c.take<int>(1);
+  const size_t io_bytes = c.total();
+  int rc = arena_reserve(io_bytes + ws_bytes);
+  if (rc != SMNNGP_OK) return rc;
+  Carver a(g_arena.dev);
+  double* dX = a.take<double>((size_t)N * D);
+  double* dy = a.take<double>(N);
+  double* dhp = a.take<double>(HP_COUNT);
+  double* dout = a.take<double>(4);
+  double* dgrad = a.take<double>(HP_COUNT);
+  int* dinfo = a.take<int>(1);
+  void* ws = static_cast<char*>(g_arena.dev) + io_bytes;
+  cudaStream_t s = g_arena.stream;
+  CU(cudaMemcpyAsync(dX, X, (size_t)N * D * 8, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(dy, y, (size_t)N * 8, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(dhp, hp, HP_COUNT * 8, cudaMemcpyHostToDevice, s));
+  rc = smnngp_lml_grad_f64(s, dX, dy, N, D, n_hidden, act, arch, dhp, kind, ws, ws_bytes, dout, dgrad, dinfo);
+  if (rc != SMNNGP_OK) return rc;
+  int hinfo = 0;
+  CU(cudaMemcpyAsync(out, dout, 4 * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(grad, dgrad, HP_COUNT * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   if (info) *info = hinfo;

@@ -104,8 +104,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS) gemm_kernel(con
     }
   }
   double acc[MI][NI][2];
-  gemm_mainloop<Cfg, ALIGN16>(acc, p.A + (long long)r0 * p.lda, p.lda, min(Cfg::BM, p.M - r0),
-                              p.B + (long long)c0 * p.ldb, p.ldb, min(Cfg::BN, p.N - c0), p.K, smem);
+  const int k0 = p.k_from_row ? r0 : 0;        // r0 is a multiple of 128: alignment of the operands is kept
+  gemm_mainloop<Cfg, ALIGN16>(acc, p.A + (long long)r0 * p.lda + k0, p.lda, min(Cfg::BM, p.M - r0),
+                              p.B + (long long)c0 * p.ldb + k0, p.ldb, min(Cfg::BN, p.N - c0), p.K - k0, smem);
   gemm_epilogue<EPI>(p, acc, r0, c0, Cfg::BM, Cfg::BN, rbase, cbase);
 }
 
@@ -118,18 +119,30 @@ struct EpiSubTma {
   }
 };
 
-cudaError_t launch_gemm_sub_tma(cudaStream_t s, const GemmParams& p) {
+// out-of-place C = A B^T (lower-masked when p.lower)
+struct EpiStoreTma {
+  using Params = GemmParams;
+  static __device__ __forceinline__ void apply(const Params& p, double (&acc)[MI][NI][2], int r0, int c0, int wm,
+                                               int wn, int lane) {
+    gemm_epilogue<EPI_STORE>(p, acc, r0, c0, TM_BM, TM_BN, r0 + wm * 64 + (lane >> 2), c0 + wn * 32 + (lane & 3) * 2);
+  }
+};
+
+template <class Epi>
+cudaError_t launch_gemm_tma(cudaStream_t s, const GemmParams& p) {
   CUtensorMap ma, mb;
   if (!make_tmap(&ma, p.A, p.M, p.K, p.lda, TM_BM) || !make_tmap(&mb, p.B, p.N, p.K, p.ldb, TM_BN))
     return cudaErrorInvalidValue;
   const int tri = p.lower && p.cyc_db == 0;
-  TmaShape sh{p.M, p.N, p.K, tri, count_tiles<TileTma>(p.M, p.N, tri), p.lower ? p.cyc_db : 0, p.cyc_p, p.base_shift};
+  TmaShape sh{p.M, p.N, p.K, tri, count_tiles<TileTma>(p.M, p.N, tri), p.lower ? p.cyc_db : 0, p.cyc_p, p.base_shift,
+              p.k_from_row};
   int sms = device_sm_count() - p.sm_reserve;
   if (sms < 8) sms = 8;
-  cudaError_t e = launch_tma_gemm<EpiSubTma>(s, ma, mb, sh, p, sms);
+  cudaError_t e = launch_tma_gemm<Epi>(s, ma, mb, sh, p, sms);
   instr().launches++;
   return e;
 }
+cudaError_t launch_gemm_sub_tma(cudaStream_t s, const GemmParams& p) { return launch_gemm_tma<EpiSubTma>(s, p); }
 
 template <typename Cfg, int EPI>
 cudaError_t launch_gemm_cfg(cudaStream_t s, const GemmParams& p) {
@@ -461,6 +474,12 @@ int debug_gemm_occupancy(int variant) {
 
 cudaError_t launch_gemm_store(cudaStream_t s, const GemmParams& p) { return launch_gemm_t<EPI_STORE>(s, p); }
 cudaError_t launch_gemm_sub(cudaStream_t s, const GemmParams& p) { return launch_gemm_t<EPI_SUB>(s, p); }
+cudaError_t launch_gemm_store_lower(cudaStream_t s, const GemmParams& p) {
+  if (p.M <= 0 || p.N <= 0) return cudaSuccess;
+  if (tile_variant() == 0 && tma_operand_ok(p.A, p.lda) && tma_operand_ok(p.B, p.ldb))
+    return launch_gemm_tma<EpiStoreTma>(s, p);
+  return launch_gemm_cfg<TilePair, EPI_STORE>(s, p);
+}
 
 long long*& potf2_clock_buffer() {
   static long long* p = nullptr;
@@ -479,9 +498,15 @@ cudaError_t launch_potf2_trtri(cudaStream_t s, double* A, long long lda, int w, 
 
 // Plain right-looking two-level factorisation on ONE stream (also the building block of the look-ahead variant,
 // where it factors the NB x NB diagonal blocks).
-static cudaError_t potrf_serial(cudaStream_t s, double* A, long long lda, long long Mtot, long long N, int NB,
+// rows touched while factoring the outer panel that ends at column c1 (see potrf_trapezoid: identity-carried rows)
+static inline long long active_rows(long long Mtot, long long ident_row0, long long c1) {
+  if (ident_row0 < 0) return Mtot;
+  return (ident_row0 + c1 < Mtot) ? ident_row0 + c1 : Mtot;
+}
+
+static cudaError_t potrf_serial(cudaStream_t s, double* A, long long lda, long long Mfull, long long N, int NB,
                                 double* Linv_base, double* logdet, int* info, long long linv_stride, int gcol_base,
-                                bool zero_linv = true) {
+                                bool zero_linv = true, long long ident_row0 = -1) {
   cudaError_t e;
   if (zero_linv) {     // the diagonal kernel only writes the lower part of each inverse block
     const long long blocks = linv_stride == 0 ? 1 : (N + PB - 1) / PB;
@@ -490,6 +515,7 @@ static cudaError_t potrf_serial(cudaStream_t s, double* A, long long lda, long l
   }
   for (long long c0 = 0; c0 < N; c0 += NB) {
     const long long c1 = (c0 + NB < N) ? c0 + NB : N;
+    const long long Mtot = active_rows(Mfull, ident_row0, c1);
     for (long long j0 = c0; j0 < c1; j0 += PB) {
       const long long j1 = (j0 + PB < N) ? j0 + PB : N;
       const int w = (int)(j1 - j0);
@@ -571,13 +597,15 @@ int& lookahead_mode() {
   return v;
 }
 
-cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long Mtot, long long N, int NB,
-                            double* Linv_base, double* logdet, int* info, long long linv_stride) {
+cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long Mfull, long long N, int NB,
+                            double* Linv_base, double* logdet, int* info, long long linv_stride,
+                            long long ident_row0) {
   if (NB < PB) NB = PB;
   NB = (NB / PB) * PB;
   if (NB > LINV_BLOCKS * PB) NB = LINV_BLOCKS * PB;
   LookaheadCtx* la = (lookahead_mode() != 0 && linv_stride == 0 && N > NB) ? lookahead_ctx() : nullptr;
-  if (la == nullptr) return potrf_serial(s, A, lda, Mtot, N, NB, Linv_base, logdet, info, linv_stride, 0);
+  if (la == nullptr)
+    return potrf_serial(s, A, lda, Mfull, N, NB, Linv_base, logdet, info, linv_stride, 0, true, ident_row0);
 
 #define LA_CK(call)                 \
   do {                              \
@@ -590,6 +618,7 @@ cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long 
   for (long long c0 = 0; c0 < N; c0 += NB) {
     const long long c1 = (c0 + NB < N) ? c0 + NB : N;
     const int w = (int)(c1 - c0);
+    const long long Mtot = active_rows(Mfull, ident_row0, c1);
     // side: diagonal block (w x w) with its block inverses
     LA_CK(potrf_serial(la->side, A + c0 * lda + c0, lda, w, w, NB, Linv_base, logdet, info, ls, (int)c0, c0 == 0));
     LA_CK(cudaEventRecord(la->ev_diag, la->side));

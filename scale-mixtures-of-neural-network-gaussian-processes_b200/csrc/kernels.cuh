@@ -47,6 +47,7 @@ struct GemmParams {
   // global rows are shifted by (cyc_p - 1) * cyc_db per block; cyc_db == 0 -> plain lower triangle
   int cyc_db, cyc_p, base_shift;
   int sm_reserve;     // persistent kernel leaves this many SMs free (look-ahead work on another stream)
+  int k_from_row;     // 1: contraction of the tile whose first row is r0 starts at k = r0 (operands upper triangular)
 };
 
 // largest active column of local row r (rows are non-decreasing in this limit)
@@ -75,8 +76,14 @@ cudaError_t launch_gemm_sub(cudaStream_t s, const GemmParams& p);
 // Blocked right-looking Cholesky of the leading N x N of the row-major trapezoid A [Mtot, N] (lower part);
 // rows N..Mtot-1 are carried along and end up as (rows) * L^-T.  NB = outer panel (multiple of 128).
 // linv_stride = 0: Linv_ws (128x128) is reused by every inner step; otherwise step k writes Linv_ws + k*linv_stride
+// ident_row0 >= 0: rows ident_row0 .. ident_row0 + N - 1 of A start as the identity (the caller wrote it) and end up
+// as U = L^-T (upper triangular).  Identity row i stays e_i until the panel that contains column i, so while
+// factoring panel [c0, c1) only carried rows below ident_row0 + c1 are touched (N^3/3 flop instead of N^3).
 cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long Mtot, long long N, int NB,
-                            double* Linv_ws, double* logdet, int* info, long long linv_stride = 0);
+                            double* Linv_ws, double* logdet, int* info, long long linv_stride = 0,
+                            long long ident_row0 = -1);
+// C = A B^T, lower part only, C does not alias the operands (TMA-fed persistent kernel when the operands allow)
+cudaError_t launch_gemm_store_lower(cudaStream_t s, const GemmParams& p);
 
 // ---- reductions / closed forms ---------------------------------------------------------------------------
 cudaError_t launch_sumsq(cudaStream_t s, const double* z, long long n, double* out);
@@ -93,6 +100,24 @@ cudaError_t launch_test_nll_finalize(cudaStream_t s, const double* mean, const d
                                      int kind, const double* quad2, const int* info, double* logp,
                                      double* nll_out);
 cudaError_t launch_fill_nan_if_bad(cudaStream_t s, const int* info, double* buf, long long n);
+
+// ---- gradient of the log marginal likelihood (grad.cu) -------------------------------------------------------
+// tab3 [3][n_act][tab_ld]: encoded marginal variances + the two dual planes the gradient epilogue needs
+cudaError_t launch_qtable_dual(cudaStream_t s, const double* X, long long ldx, int N, int D, int n_hidden, int act,
+                               int arch, const double* hp, double* tab3, long long tab_ld);
+// A [N, lda] <- identity (zero fill + ones)
+cudaError_t launch_set_identity(cudaStream_t s, double* A, long long lda, long long N);
+// out_i = sum_{k >= i} U[i,k] z[k]
+cudaError_t launch_upper_gemv(cudaStream_t s, const double* U, long long ldu, const double* z, long long N,
+                              double* out);
+long long grad_partial_slots(long long N);
+// partial[slots][4] = per-warp sums of G_ij dK_ij/d(w_std, b_std, last_w_std) and tr G over the lower triangle
+cudaError_t launch_grad_gram(cudaStream_t s, const double* X, long long N, long long D, int n_hidden, int act,
+                             int arch, const double* hp, const double* tab3, long long tab_ld, const double* Winv,
+                             long long ldw, const double* alpha, const double* quad, int kind, double* partial,
+                             long long slots);
+cudaError_t launch_grad_finalize(cudaStream_t s, const double* partial, long long slots, const double* hp,
+                                 const double* quad, int kind, long long N, const int* info, double* grad);
 
 // ---- instrumentation (bench.py): kernel-launch counter and CUDA-event timing of the trailing updates -------
 struct Instrumentation {

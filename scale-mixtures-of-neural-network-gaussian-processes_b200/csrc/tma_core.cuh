@@ -38,6 +38,9 @@ struct TmaShape {
   long long tiles;
   // block-row-cyclic mask (multi-GPU local update, see GemmParams): rectangular enumeration, inactive tiles skipped
   int cyc_db, cyc_p, base_shift;
+  // 1: both operands are rows of an UPPER-triangular matrix (zero left of the diagonal) and the tile list is the
+  // lower triangle, so the contraction of tile (r0, c0) only runs over k >= r0 (A^-1 = U U^T with U = L^-T)
+  int k_from_row;
 };
 
 __device__ __forceinline__ bool tma_tile_active(const TmaShape& sh, int r0, int c0) {
@@ -159,7 +162,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         decode_tile<2>(t, ntn, sh.lower, ti, tj);
         const int r0 = ti * TM_BM, c0 = tj * TM_BN;
         if (!tma_tile_active(sh, r0, c0)) continue;
-        for (int kt = 0; kt < KT; kt++) {
+        for (int kt = sh.k_from_row ? r0 / BK : 0; kt < KT; kt++) {
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           mbar_arrive_expect_tx(full0 + 8 * s, TM_STAGE_BYTES);
           const uint32_t dst = gring + s * TM_STAGE_BYTES;
@@ -193,7 +196,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
       for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-    for (int kt = 0; kt < KT; kt++) {
+    for (int kt = sh.k_from_row ? ti * (TM_BM / BK) : 0; kt < KT; kt++) {
       mbar_wait(full0 + 8 * s, ph);
       const uint32_t st = gring + s * TM_STAGE_BYTES;
       double a[2][MI], b[2][NI];

@@ -187,6 +187,40 @@ def lml(x, y, *, spec: StackSpec, hp, kind="student_t"):
     return out, info
 
 
+def lml_grad(x, y, *, spec: StackSpec, hp, kind="student_t"):
+    """SPR.loss and d loss / d {w_std, b_std, last_w_std, eps, alpha, beta} in one call - the value/gradient pair
+    objax.GradValues(model.loss, vars) produces in regression/train.py:62-66 (before the softplus chain rule).
+    Device inputs -> (out[4], grad[6], info) device tensors; NumPy inputs -> host entry point."""
+    lib = _lib.load()
+    nh, act, arch = spec.ids()
+    if isinstance(x, np.ndarray):
+        _require_cuda()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        hp = np.ascontiguousarray(hp, dtype=np.float64)
+        out = np.empty(4, dtype=np.float64)
+        grad = np.empty(6, dtype=np.float64)
+        info = C.c_int(0)
+        rc = lib.smnngp_lml_grad_host_f64(x.ctypes.data, y.ctypes.data, x.shape[0], x.shape[1], nh, act, arch,
+                                          hp.ctypes.data, KIND[kind], out.ctypes.data, grad.ctypes.data,
+                                          C.byref(info))
+        _lib.check(rc, "lml_grad_host")
+        return out, grad, info.value
+    _require_cuda()
+    x = _f64(x)
+    y = _f64(y, x.device)
+    n, d = x.shape
+    out = torch.empty(4, dtype=torch.float64, device=x.device)
+    grad = torch.empty(6, dtype=torch.float64, device=x.device)
+    info = torch.zeros(1, dtype=torch.int32, device=x.device)
+    ws_bytes = lib.smnngp_lml_grad_workspace_bytes(n, d, nh, arch)
+    ws = _workspace(ws_bytes, x.device)
+    rc = lib.smnngp_lml_grad_f64(_stream(x.device), _p(x), _p(y), n, d, nh, act, arch, _p(hp), KIND[kind], _p(ws),
+                                 ws_bytes, _p(out), _p(grad), _p(info))
+    _lib.check(rc, "lml_grad")
+    return out, grad, info
+
+
 class LmlGraph:
     """The fused LML call captured once into a CUDA graph and replayed - the analogue of wrapping SPR.loss in
     objax.Jit (regression/train.py:61-67): the training loop evaluates the same shapes tens of thousands of

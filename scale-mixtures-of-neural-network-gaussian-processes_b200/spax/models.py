@@ -46,6 +46,28 @@ class SPR(Module):
         log_prob = self.likelihood.prior_logpdf(self.y_data, cov)
         return -log_prob / self.num_data
 
+    def loss_and_grad(self):
+        """(loss, grads): the pair ``objax.GradValues(model.loss, model.vars())`` returns in the reference's train
+        step (experiments/regression/train.py:62-66), as one fused call.  ``grads`` maps the names of
+        ``self.vars()`` to d loss / d (unconstrained variable value) - the softplus chain rule
+        (spax/base.py:23-25, spax/bijectors.py:51-53) is applied here.  Scalars the likelihood does not own
+        (Gaussian: alpha, beta) are absent."""
+        kernel_fn = self.kernel.get_kernel_fn()
+        if not self._fused(kernel_fn):
+            raise TypeError("loss_and_grad needs a kernel_fn built by smnngp nt_kernels and a spax likelihood")
+        host = isinstance(self.x_data, np.ndarray)
+        hp = kernel_fn.hp_host(**self._hp_args()) if host else kernel_fn.hp(self.x_data.device, **self._hp_args())
+        out, grad, _ = _dev.lml_grad(self.x_data, self.y_data, spec=kernel_fn.spec, hp=hp, kind=self.likelihood.kind)
+        g = grad if host else grad.cpu().numpy()
+        loss = float(out[1])
+        slots = {"kernel.w_std": (self.kernel.w_std, 0), "kernel.b_std": (self.kernel.b_std, 1),
+                 "kernel.last_w_std": (self.kernel.last_w_std, 2), "eps": (self.eps, 3)}
+        if hasattr(self.likelihood, "a"):
+            slots["likelihood.a"] = (self.likelihood.a, 4)
+            slots["likelihood.b"] = (self.likelihood.b, 5)
+        grads = {name: float(g[i]) * float(var.constraint.grad(var.value)) for name, (var, i) in slots.items()}
+        return loss, grads
+
     def test_nll(self, x, y):
         kernel_fn = self.kernel.get_kernel_fn()
         if self._fused(kernel_fn):
