@@ -163,6 +163,14 @@ int smnngp_stage_sumsq_f64(void* stream, const double* z, int64_t n, double* out
 int smnngp_stage_lml_finalize_f64(void* stream, const double* sums_dev, const double* hp_dev, int kind, int64_t N,
                                   const int* info_dev, double* out_dev);
 
+/* ---- peer memory (multi-GPU, one process per GPU): cudaMalloc'ed buffers exported / imported as 64-byte CUDA IPC
+ * handles so that every rank can store into every other rank's panel buffer over NVLink (no reference
+ * counterpart: the reference is single-device). */
+int smnngp_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out64);
+int smnngp_peer_open(const unsigned char* handle64, void** ptr_out);
+int smnngp_peer_close(void* ptr);
+int smnngp_peer_free(void* ptr);
+
 /* ---- host-buffer entry points (what a ctypes / cgo / JNI caller without device arrays binds): inputs and
  * outputs are HOST pointers; device staging comes from a grow-only arena released by smnngp_host_release(). */
 int smnngp_lml_host_f64(const double* X, const double* y, int64_t N, int64_t D, int n_hidden, int act, int arch,

@@ -136,6 +136,7 @@ cudaError_t launch_gemm_tma(cudaStream_t s, const GemmParams& p) {
   const int tri = p.lower && p.cyc_db == 0;
   TmaShape sh{p.M, p.N, p.K, tri, count_tiles<TileTma>(p.M, p.N, tri), p.lower ? p.cyc_db : 0, p.cyc_p, p.base_shift,
               p.k_from_row};
+  if (sh.cyc_db != 0) sh.tiles = tma_cyc_count_tiles(sh);       // active tiles only
   int sms = device_sm_count() - p.sm_reserve;
   if (sms < 8) sms = 8;
   cudaError_t e = launch_tma_gemm<Epi>(s, ma, mb, sh, p, sms);

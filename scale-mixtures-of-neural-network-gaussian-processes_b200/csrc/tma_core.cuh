@@ -43,11 +43,41 @@ struct TmaShape {
   int k_from_row;
 };
 
-__device__ __forceinline__ bool tma_tile_active(const TmaShape& sh, int r0, int c0) {
-  if (sh.cyc_db == 0) return true;
-  const int rl = min(r0 + TM_BM, sh.M) - 1;
+// Block-row-cyclic mask: number of column tiles of row tile ti that touch the active region (a prefix of the row,
+// the limit grows with the row).  Only these tiles are enumerated, so the static tile -> CTA assignment stays
+// balanced (a rectangular enumeration that merely skipped the inactive half left some CTAs with up to 2x the
+// work of others late in the factorisation).
+__host__ __device__ __forceinline__ int tma_cyc_row_tiles(const TmaShape& sh, int ti, int ntn) {
+  const int rl = (ti * TM_BM + TM_BM < sh.M ? ti * TM_BM + TM_BM : sh.M) - 1;
   const long long lim = (long long)rl + sh.base_shift + (long long)(rl / sh.cyc_db) * (sh.cyc_p - 1) * sh.cyc_db;
-  return c0 <= lim;
+  if (lim < 0) return 0;
+  const long long c = lim / TM_BN + 1;
+  return c < ntn ? (int)c : ntn;
+}
+inline long long tma_cyc_count_tiles(const TmaShape& sh) {
+  const int ntm = (sh.M + TM_BM - 1) / TM_BM, ntn = (sh.N + TM_BN - 1) / TM_BN;
+  long long t = 0;
+  for (int ti = 0; ti < ntm; ti++) t += tma_cyc_row_tiles(sh, ti, ntn);
+  return t;
+}
+// Tile ids handed to one warp only grow, so the row of a tile id is found by walking a cursor forward.
+struct TileCursor {
+  int ti = 0;
+  long long base = 0;      // active tiles in rows < ti
+};
+__device__ __forceinline__ void tma_decode(const TmaShape& sh, long long t, int ntn, TileCursor& cur, int& ti,
+                                           int& tj) {
+  if (sh.cyc_db == 0) {
+    decode_tile<2>(t, ntn, sh.lower, ti, tj);
+    return;
+  }
+  int cnt = tma_cyc_row_tiles(sh, cur.ti, ntn);
+  while (t >= cur.base + cnt) {
+    cur.base += cnt;
+    cnt = tma_cyc_row_tiles(sh, ++cur.ti, ntn);
+  }
+  ti = cur.ti;
+  tj = (int)(t - cur.base);
 }
 
 // ---- host: tensor map for a row-major [rows, inner] FP64 operand (row pitch ld doubles) ---------------------
@@ -157,11 +187,11 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const uint32_t full0 = bars + 8 * (g * TM_STAGES), empty0 = bars + 8 * (2 * TM_STAGES + g * TM_STAGES);
       int s = 0;
       uint32_t ph = 0;
+      TileCursor cur;
       for (long long t = 2ll * blockIdx.x + g; t < sh.tiles; t += stride) {
         int ti, tj;
-        decode_tile<2>(t, ntn, sh.lower, ti, tj);
+        tma_decode(sh, t, ntn, cur, ti, tj);
         const int r0 = ti * TM_BM, c0 = tj * TM_BN;
-        if (!tma_tile_active(sh, r0, c0)) continue;
         for (int kt = sh.k_from_row ? r0 / BK : 0; kt < KT; kt++) {
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           mbar_arrive_expect_tx(full0 + 8 * s, TM_STAGE_BYTES);
@@ -186,10 +216,10 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t b_off = (uint32_t)(TM_A_BYTES + (wn * 32 + g8) * 128) + off0;
   int s = 0, prev_stage = -1;
   uint32_t ph = 0;
+  TileCursor cur;
   for (long long t = 2ll * blockIdx.x + g; t < sh.tiles; t += stride) {
     int ti, tj;
-    decode_tile<2>(t, ntn, sh.lower, ti, tj);
-    if (!tma_tile_active(sh, ti * TM_BM, tj * TM_BN)) continue;
+    tma_decode(sh, t, ntn, cur, ti, tj);
     double acc[MI][NI][2];
 #pragma unroll
     for (int mi = 0; mi < MI; mi++)

@@ -154,11 +154,20 @@ class DistributedLML:
     """SPR.loss (spax/models.py:93-98) sharded over the ranks of a process group.  Strong scaling: the problem
     is fixed, every rank owns ~1/P of the rows."""
 
-    def __init__(self, n, d, spec: StackSpec, device, group=None, block=None, backend=None):
+    def __init__(self, n, d, spec: StackSpec, device, group=None, block=None, backend=None, emulate=None):
+        """emulate=(world, rank): timing dry-run of ONE rank's work of a `world`-rank job on a single device - the
+        collectives are replaced by local copies of the same size, so the numbers it produces are meaningless but
+        every kernel launch has the shape it has in the real job (used to profile the schedule at 1 GPU cost)."""
         self.n, self.d, self.spec = int(n), int(d), spec
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.emulate = emulate is not None
+        if self.emulate:
+            self.world, self.rank = int(emulate[0]), int(emulate[1])
+        else:
+            self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.timeline = None          # list of (panel, label, event) when profiling is switched on
+        self._gidx = {}
         self.db = int(block) if block else default_block(self.n, self.world)
         self.be = backend if backend is not None else CudaBackend(device)
         self.lay = BlockRowCyclic(self.n + 1, self.n, self.world, self.rank, self.db)
@@ -177,6 +186,7 @@ class DistributedLML:
         # SMs the bulk update leaves free so the look-ahead chain (diagonal block, TRSM, NCCL) really overlaps:
         # the persistent update kernel otherwise occupies every SM until it ends
         self.sm_reserve = int(os.environ.get("SMNNGP_SM_RESERVE", "8" if self.world > 1 else "0"))
+        self.reserve_below_s = float(os.environ.get("SMNNGP_RESERVE_BELOW_MS", "18")) * 1e-3
 
     # ---- stages ----------------------------------------------------------------------------------------------
     def _build_gram(self, x, y, hp):
@@ -198,12 +208,22 @@ class DistributedLML:
 
     def _gather_index(self, p, c1):
         """position of global rows [c1, N) inside the padded all-gather buffer (rank-major)"""
-        lay, db, P = self.lay, self.db, self.world
-        gr = torch.arange(c1, self.n, device=self.a.device, dtype=torch.int64)
-        gb = gr // db
-        r = gb % P
-        fb = (p + 1) + ((r - (p + 1)) % P)
-        return r * max(self.max_m, 1) + ((gb - fb) // P) * db + gr % db
+        idx = self._gidx.get(p)
+        if idx is None:                 # depends on the layout only: built once, reused by every evaluation
+            db, P = self.db, self.world
+            gr = torch.arange(c1, self.n, device=self.a.device, dtype=torch.int64)
+            gb = gr // db
+            r = gb % P
+            fb = (p + 1) + ((r - (p + 1)) % P)
+            idx = r * max(self.max_m, 1) + ((gb - fb) // P) * db + gr % db
+            self._gidx[p] = idx
+        return idx
+
+    def _mark(self, p, label):
+        if self.timeline is not None and self.a.is_cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.timeline.append((p, label, ev))
 
     # ---- one panel: diagonal block, broadcast, TRSM of the local rows, all-gather of the panel ---------------
     def _panel(self, p, sums, info, slot):
@@ -221,9 +241,11 @@ class DistributedLML:
             blk = self.a[lo:lo + w, c0:c1]
             be.factor_diag(blk, linv, sums[0:1], info, c0)
             ldiag.copy_(blk)
-        if P > 1:
+        self._mark(p, "diag")
+        if P > 1 and not self.emulate:
             dist.broadcast(self.diag, src=dist.get_global_rank(self.group, owner) if self.group else owner,
                            group=self.group)
+        self._mark(p, "bcast")
         # this rank's rows with global index >= c1: on the owner whatever follows the diagonal rows (the rest of
         # block p, i.e. the appended row when the block straddles N, then its later blocks), elsewhere all
         # local blocks >= p + 1.  Both are suffixes of the local storage.
@@ -234,14 +256,20 @@ class DistributedLML:
             ls, m = lay.rows_from_block(p + 1)
         if m > 0:
             be.trsm(self.a[ls:ls + m, c0:c1], ldiag, linv)
+        self._mark(p, "trsm")
         if c1 >= n:
             return ls, m, None
         if P > 1:
             if m > 0:
                 self.send[:m, :w].copy_(self.a[ls:ls + m, c0:c1])
-            dist.all_gather_into_tensor(self.gath, self.send, group=self.group)
+            if self.emulate:
+                self.gath.view(P, -1, self.db).copy_(self.send.unsqueeze(0).expand(P, -1, -1))
+            else:
+                dist.all_gather_into_tensor(self.gath, self.send, group=self.group)
+            self._mark(p, "gather")
             pfull = self.pfull[slot][:n - c1]
             torch.index_select(self.gath, 0, self._gather_index(p, c1), out=pfull)
+            self._mark(p, "reorder")
         else:
             pfull = self.a[ls:ls + (n - c1), c0:c1]
         return ls, m, pfull
@@ -274,6 +302,7 @@ class DistributedLML:
             ls, m, pfull = cur
             if cuda:
                 main.wait_event(ev_panel)                                  # panel p is factored and gathered
+            self._mark(p, "main_start")
             if c1 >= n:
                 break
             w = c1 - c0
@@ -282,6 +311,7 @@ class DistributedLML:
             na = min(db, n - c1)                                           # next panel's block column first
             if m > 0:
                 be.update(self.a[ls:ls + m, c0:c1], pfull[:na], self.a[ls:ls + m, c1:c1 + na], True, db, P, shift)
+            self._mark(p, "update_a")
             if cuda:
                 ev_a = torch.cuda.Event()
                 ev_a.record(main)
@@ -296,7 +326,8 @@ class DistributedLML:
                 # 5 % of the update): estimated update time at 33 TFLOP/s below 18 ms
                 t_est = 2.0 * m * (n - c1 - na) * w / 33e12
                 be.update(self.a[ls:ls + m, c0:c1], pfull[na:], self.a[ls:ls + m, c1 + na:n], True, db, P,
-                          shift - na, self.sm_reserve if t_est < 18e-3 else 0)
+                          shift - na, self.sm_reserve if t_est < self.reserve_below_s else 0)
+            self._mark(p, "update_b")
             cur = nxt
         if cuda:
             main.wait_stream(side)
@@ -305,7 +336,7 @@ class DistributedLML:
         if self.rank == lay.owner(bn):
             lrow = lay.local_offset(bn) + (n - bn * db)
             be.sumsq(self.a[lrow, :n], sums[1:2])
-        if P > 1:
+        if P > 1 and not self.emulate:
             dist.all_reduce(sums, group=self.group)
             dist.all_reduce(info, op=dist.ReduceOp.MAX, group=self.group)
         return be.lml_finalize(sums, hp, kind, n, info), info
