@@ -163,6 +163,33 @@ int smnngp_stage_sumsq_f64(void* stream, const double* z, int64_t n, double* out
 int smnngp_stage_lml_finalize_f64(void* stream, const double* sums_dev, const double* hp_dev, int kind, int64_t N,
                                   const int* info_dev, double* out_dev);
 
+/* ---- multi-GPU panel exchange by peer stores over NVLink (csrc/exchange.cu; replaces one ncclBroadcast + one
+ * ncclAllGather per panel).  Pointer arrays are HOST arrays of P device pointers (index = rank), read at call time.
+ *   factor_diag_inv : factor the diagonal block inside the scratch T [2w, w] with identity rows carried along:
+ *                     T rows 0..w-1 = L, rows w..2w-1 = L^-T (A is only read)
+ *   scatter_inverse : W = inv(L) = (L^-T)^T, lower triangular row-major, stored into every rank's buffer, then the
+ *                     flag word `flag_index` of every rank is set to seq
+ *   trsm_scatter    : Ploc = R W^T (tensor pipe, one launch) and the same rows stored at (global row - c1) of every
+ *                     rank's panel buffer; the last CTA sets flag word `flag_index` on every rank to seq
+ *   signal / wait_flags : raise a flag on every rank / one-thread spin until flags[first .. first+count) >= seq;
+ *                     after timeout_s the wait gives up and sets *info_dev = INT_MAX (results become NaN) so a dead
+ *                     peer cannot hang the device */
+int smnngp_stage_factor_diag_inv_f64(void* stream, const double* A, int64_t lda, int64_t w, double* T,
+                                     double* linv_ws, double* logdet_dev, int* info_dev, int64_t gcol0);
+int smnngp_stage_scatter_inverse_f64(void* stream, const double* Ut, int64_t ldu, int64_t w, void* const* dst_ptrs,
+                                     int P, int64_t ldw, void* const* flag_ptrs, int64_t flag_index, uint64_t seq,
+                                     unsigned int* counter);
+int smnngp_stage_signal_f64(void* stream, void* const* flag_ptrs, int P, int64_t flag_index, uint64_t seq);
+int smnngp_stage_wait_flags_f64(void* stream, const void* flags_local, int64_t first, int count, uint64_t seq,
+                                double timeout_s, int* info_dev);
+/* how wait_flags waits: 0 (default) = cuStreamWaitValue64 on the stream (no SM occupied, no timeout), 1 = one-thread
+ * spin kernel with the timeout described above */
+void smnngp_set_peer_wait_mode(int mode);
+int smnngp_stage_trsm_scatter_f64(void* stream, const double* R, int64_t ldr, int64_t m, int64_t w, const double* W,
+                                  int64_t ldw, double* Ploc, int64_t ldp, void* const* peer_ptrs, int P, int rank,
+                                  int64_t db, int64_t local_row0, int64_t c1, int64_t n, int64_t ld_peer,
+                                  void* const* flag_ptrs, int64_t flag_index, uint64_t seq, unsigned int* counter);
+
 /* ---- peer memory (multi-GPU, one process per GPU): cudaMalloc'ed buffers exported / imported as 64-byte CUDA IPC
  * handles so that every rank can store into every other rank's panel buffer over NVLink (no reference
  * counterpart: the reference is single-device). */

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsmnngp.so")
-SOURCES = ["gram.cu", "chol.cu", "reduce.cu", "api.cu", "stages.cu", "draws.cu", "grad.cu", "peer.cu"]
+SOURCES = ["gram.cu", "chol.cu", "reduce.cu", "api.cu", "stages.cu", "draws.cu", "grad.cu", "peer.cu", "exchange.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets"]
 
@@ -29,6 +29,8 @@ EXPORTS = [
     "smnngp_sample_f_iid_f64", "smnngp_draw_metrics_f64",
     "smnngp_stage_qtable_f64", "smnngp_stage_gram_f64", "smnngp_stage_factor_diag_f64", "smnngp_stage_trsm_f64",
     "smnngp_stage_update_f64", "smnngp_stage_sumsq_f64", "smnngp_stage_lml_finalize_f64",
+    "smnngp_stage_factor_diag_inv_f64", "smnngp_stage_scatter_inverse_f64", "smnngp_stage_signal_f64",
+    "smnngp_stage_wait_flags_f64", "smnngp_stage_trsm_scatter_f64", "smnngp_set_peer_wait_mode",
     "smnngp_peer_alloc", "smnngp_peer_open", "smnngp_peer_close", "smnngp_peer_free",
     "smnngp_instr_reset", "smnngp_instr_launches", "smnngp_instr_updates", "smnngp_dmma_peak_tflops",
 ]
@@ -138,6 +140,15 @@ def _declare(lib):
                                             _i64, _i]
     lib.smnngp_stage_sumsq_f64.argtypes = [_vp, _vp, _i64, _vp]
     lib.smnngp_stage_lml_finalize_f64.argtypes = [_vp, _vp, _vp, _i, _i64, _vp, _vp]
+    _u64, _u = C.c_uint64, C.c_int
+    lib.smnngp_stage_factor_diag_inv_f64.argtypes = [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64]
+    lib.smnngp_stage_scatter_inverse_f64.argtypes = [_vp, _vp, _i64, _i64, _vp, _i, _i64, _vp, _i64, _u64, _vp]
+    lib.smnngp_stage_signal_f64.argtypes = [_vp, _vp, _i, _i64, _u64]
+    lib.smnngp_stage_wait_flags_f64.argtypes = [_vp, _vp, _i64, _i, _u64, _d, _vp]
+    lib.smnngp_stage_trsm_scatter_f64.argtypes = [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i,
+                                                  _i64, _i64, _i64, _i64, _i64, _vp, _i64, _u64, _vp]
+    lib.smnngp_set_peer_wait_mode.restype = None
+    lib.smnngp_set_peer_wait_mode.argtypes = [_i]
     lib.smnngp_peer_alloc.argtypes = [_sz, _vp, _vp]
     lib.smnngp_peer_open.argtypes = [_vp, _vp]
     lib.smnngp_peer_close.argtypes = [_vp]

@@ -523,12 +523,14 @@ static cudaError_t potrf_serial(cudaStream_t s, double* A, long long lda, long l
       double* Linv_ws = Linv_base + (j0 / PB) * linv_stride;
       e = launch_potf2_trtri(s, A + j0 * lda + j0, lda, w, Linv_ws, logdet, info, gcol_base + (int)j0);
       if (e != cudaSuccess) return e;
-      if (Mtot > j1) {
+      // identity-carried rows below ident_row0 + j1 are the only ones with entries in this 128-block so far
+      const long long Mj = active_rows(Mfull, ident_row0, j1);
+      if (Mj > j1) {
         GemmParams t{};   // panel rows <- panel rows * inv(L_jj)^T   (in place: one CTA owns whole rows)
         t.A = A + j1 * lda + j0; t.lda = lda;
         t.B = Linv_ws;           t.ldb = PB;
         t.C = A + j1 * lda + j0; t.ldc = lda;
-        t.M = (int)(Mtot - j1); t.N = w; t.K = w; t.lower = 0;
+        t.M = (int)(Mj - j1); t.N = w; t.K = w; t.lower = 0;
         e = launch_gemm_store(s, t);
         if (e != cudaSuccess) return e;
         if (j1 < c1) {    // remaining columns of the outer panel
@@ -536,7 +538,7 @@ static cudaError_t potrf_serial(cudaStream_t s, double* A, long long lda, long l
           u.A = A + j1 * lda + j0; u.lda = lda;
           u.B = A + j1 * lda + j0; u.ldb = lda;
           u.C = A + j1 * lda + j1; u.ldc = lda;
-          u.M = (int)(Mtot - j1); u.N = (int)(c1 - j1); u.K = w; u.lower = 1;
+          u.M = (int)(Mj - j1); u.N = (int)(c1 - j1); u.K = w; u.lower = 1;
           e = launch_gemm_sub(s, u);
           if (e != cudaSuccess) return e;
         }

@@ -20,6 +20,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace smnngp {
@@ -41,6 +43,9 @@ struct TmaShape {
   // 1: both operands are rows of an UPPER-triangular matrix (zero left of the diagonal) and the tile list is the
   // lower triangle, so the contraction of tile (r0, c0) only runs over k >= r0 (A^-1 = U U^T with U = L^-T)
   int k_from_row;
+  // 1: operand B is LOWER triangular (row j zero right of column j), so the contraction of the tile whose first
+  // column is c0 only runs over k < c0 + 64 (panel solve with the explicit inverse: rows * inv(L)^T)
+  int k_upto_col;
 };
 
 // Block-row-cyclic mask: number of column tiles of row tile ti that touch the active region (a prefix of the row,
@@ -154,6 +159,18 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   return v;
 }
 
+// optional Epi::finish(params): run once per CTA by the 256 math threads after the last tile (e.g. cross-GPU signal)
+template <class Epi, class = void>
+struct epi_has_finish : std::false_type {};
+template <class Epi>
+struct epi_has_finish<Epi, std::void_t<decltype(&Epi::finish)>> : std::true_type {};
+
+__device__ __forceinline__ int tma_kt_end(const TmaShape& sh, int KT, int c0) {
+  if (!sh.k_upto_col) return KT;
+  const int e = (c0 + TM_BN + BK - 1) / BK;
+  return e < KT ? e : KT;
+}
+
 // Epi must provide:  struct Params;  static __device__ void apply(const Params&, double (&acc)[MI][NI][2],
 //                    int r0, int c0, int wm, int wn, int lane);   (r0, c0 = tile origin; wm, wn in {0, 1})
 template <class Epi>
@@ -192,7 +209,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         int ti, tj;
         tma_decode(sh, t, ntn, cur, ti, tj);
         const int r0 = ti * TM_BM, c0 = tj * TM_BN;
-        for (int kt = sh.k_from_row ? r0 / BK : 0; kt < KT; kt++) {
+        const int kt_end = tma_kt_end(sh, KT, c0);
+        for (int kt = sh.k_from_row ? r0 / BK : 0; kt < kt_end; kt++) {
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           mbar_arrive_expect_tx(full0 + 8 * s, TM_STAGE_BYTES);
           const uint32_t dst = gring + s * TM_STAGE_BYTES;
@@ -226,7 +244,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
       for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-    for (int kt = sh.k_from_row ? ti * (TM_BM / BK) : 0; kt < KT; kt++) {
+    const int kt_end = tma_kt_end(sh, KT, tj * TM_BN);
+    for (int kt = sh.k_from_row ? ti * (TM_BM / BK) : 0; kt < kt_end; kt++) {
       mbar_wait(full0 + 8 * s, ph);
       const uint32_t st = gring + s * TM_STAGE_BYTES;
       double a[2][MI], b[2][NI];
@@ -264,6 +283,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     prev_stage = -1;
     Epi::apply(ep, acc, ti * TM_BM, tj * TM_BN, wm, wn, lane);
   }
+  if constexpr (epi_has_finish<Epi>::value) Epi::finish(ep);
 }
 
 template <class Epi>

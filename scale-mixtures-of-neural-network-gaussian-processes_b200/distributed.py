@@ -140,6 +140,71 @@ class CudaBackend:
         return out
 
 
+class _RawCuda:
+    """torch view of a raw device pointer (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=3)
+
+
+class PeerExchange:
+    """Peer-visible buffers of the panel exchange (csrc/exchange.cu): every rank cudaMalloc's one region
+    [W | flags | 3 panel slots], exports it as a CUDA IPC handle, and opens everybody else's, so kernels can store
+    straight into the other GPUs over NVLink.  emulate: all "peers" alias the local region (timing dry-run)."""
+
+    FLAG_WORDS = 16                       # word 0: W-ready (set by the panel owner); words 8..15: panel-ready per rank
+
+    def __init__(self, lib, device, world, rank, group, n, db, emulate=False):
+        self.lib, self.world, self.rank, self.db, self.n = lib, world, rank, db, n
+        self.off_w = 0
+        self.off_flags = db * db * 8
+        self.off_panel = self.off_flags + 256
+        self.slot_bytes = n * db * 8
+        total = self.off_panel + 3 * self.slot_bytes
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        if lib.smnngp_peer_alloc(total, C.byref(ptr), handle) != 0:
+            raise RuntimeError("smnngp_peer_alloc failed: " + lib.smnngp_last_error().decode())
+        self.local = ptr.value
+        self._opened = []
+        torch.as_tensor(_RawCuda(self.local + self.off_flags, (32,), "<i8"), device=device).zero_()
+        if emulate or world == 1:
+            self.bases = [self.local] * world
+        else:
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine, group=group)          # also orders the zeroing above before any peer store
+            self.bases = []
+            for r in range(world):
+                if r == rank:
+                    self.bases.append(self.local)
+                    continue
+                q, hh = C.c_void_p(), (C.c_ubyte * 64)(*allh[r].cpu().tolist())
+                if lib.smnngp_peer_open(hh, C.byref(q)) != 0:
+                    raise RuntimeError(f"smnngp_peer_open(rank {r}) failed: CUDA IPC unavailable")
+                self._opened.append(q.value)
+                self.bases.append(q.value)
+            torch.cuda.synchronize(device)
+            dist.barrier(group=group)
+        self.w_local = torch.as_tensor(_RawCuda(self.local + self.off_w, (db, db), "<f8"), device=device)
+        self.panel_local = [torch.as_tensor(_RawCuda(self.local + self.off_panel + k * self.slot_bytes, (n, db), "<f8"),
+                                            device=device) for k in range(3)]
+        self.flags_local = C.c_void_p(self.local + self.off_flags)
+        self.w_ptrs = self._arr(self.off_w)
+        self.flag_ptrs = self._arr(self.off_flags)
+        self.panel_ptrs = [self._arr(self.off_panel + k * self.slot_bytes) for k in range(3)]
+
+    def _arr(self, off):
+        return (C.c_void_p * self.world)(*[b + off for b in self.bases])
+
+    def close(self):
+        for p in self._opened:
+            self.lib.smnngp_peer_close(C.c_void_p(p))
+        self._opened = []
+        if self.local:
+            self.lib.smnngp_peer_free(C.c_void_p(self.local))
+            self.local = 0
+
+
 def default_block(n, world):
     """distribution block = outer panel width: wide enough for the update kernel, small enough to balance"""
     per_rank = n / max(world, 1)
@@ -154,7 +219,8 @@ class DistributedLML:
     """SPR.loss (spax/models.py:93-98) sharded over the ranks of a process group.  Strong scaling: the problem
     is fixed, every rank owns ~1/P of the rows."""
 
-    def __init__(self, n, d, spec: StackSpec, device, group=None, block=None, backend=None, emulate=None):
+    def __init__(self, n, d, spec: StackSpec, device, group=None, block=None, backend=None, emulate=None,
+                 exchange="auto"):
         """emulate=(world, rank): timing dry-run of ONE rank's work of a `world`-rank job on a single device - the
         collectives are replaced by local copies of the same size, so the numbers it produces are meaningless but
         every kernel launch has the shape it has in the real job (used to profile the schedule at 1 GPU cost)."""
@@ -167,6 +233,8 @@ class DistributedLML:
             self.world = dist.get_world_size(group) if dist.is_initialized() else 1
             self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.timeline = None          # list of (panel, label, event) when profiling is switched on
+        self._dbg_events = int(os.environ.get("SMNNGP_MAIN_EVENTS", "0"))
+        self._tl_filter = None
         self._gidx = {}
         self.db = int(block) if block else default_block(self.n, self.world)
         self.be = backend if backend is not None else CudaBackend(device)
@@ -178,10 +246,28 @@ class DistributedLML:
         self.diag = self.be.empty(self.db * self.db + nblk * PB * PB)
         # largest per-rank panel piece over all panels (panel p -> rows in blocks >= p + 1)
         self.max_m = max(self.lay.rows_from_block(1, r)[1] for r in range(self.world)) if self.world > 1 else 0
-        self.send = self.be.empty(max(self.max_m, 1), self.db) if self.world > 1 else None
-        self.gath = self.be.empty(self.world * max(self.max_m, 1), self.db) if self.world > 1 else None
-        # panel in global row order, double buffered (look-ahead prepares panel p + 1 while panel p is in use)
-        self.pfull = [self.be.empty(self.n, self.db) for _ in range(2)] if self.world > 1 else None
+        self._nccl_bufs = False
+        # panel exchange: "peer" = stores into the other ranks' buffers over NVLink (csrc/exchange.cu), "nccl" =
+        # broadcast + all-gather (also the path the CPU suite drives under gloo with the NumPy backend)
+        peer_ok = self.a.is_cuda and isinstance(self.be, CudaBackend) and 1 < self.world <= 8
+        if exchange == "auto":
+            exchange = os.environ.get("SMNNGP_EXCHANGE", "peer" if peer_ok else "nccl")
+        if exchange == "peer" and not peer_ok:
+            raise ValueError("exchange='peer' needs CUDA, the C-ABI backend and 2..8 ranks")
+        self.exchange = exchange
+        self.px = None
+        if exchange == "peer":
+            self.px = PeerExchange(self.be.lib, self.a.device, self.world, self.rank, group, self.n, self.db,
+                                   emulate=self.emulate)
+            self.tdiag = self.be.empty(2 * self.db * self.db)            # owner's factorisation scratch [2w, w]
+            self.linv4 = self.be.empty(nblk * PB * PB)
+            self.ploc = [self.be.empty(max(self.mloc, 1), self.db) for _ in range(2)]
+            self.counters = torch.zeros(8, dtype=torch.int32, device=self.a.device)
+            self.zvec = self.be.zeros(self.n)
+            self.seq_base = 0
+            self.send = self.gath = self.pfull = None
+            self.wait_timeout_s = float(os.environ.get("SMNNGP_PEER_TIMEOUT_S", "20"))
+            self.be.lib.smnngp_set_peer_wait_mode(int(os.environ.get("SMNNGP_PEER_WAIT", "0")))
         self.side = torch.cuda.Stream(device=self.a.device, priority=-1) if self.a.is_cuda else None
         # SMs the bulk update leaves free so the look-ahead chain (diagonal block, TRSM, NCCL) really overlaps:
         # the persistent update kernel otherwise occupies every SM until it ends
@@ -220,13 +306,87 @@ class DistributedLML:
         return idx
 
     def _mark(self, p, label):
-        if self.timeline is not None and self.a.is_cuda:
+        if self._dbg_events and self.a.is_cuda:
+            if (label == "update_a" and self._dbg_events in (2, 3)) or (label == "update_b" and self._dbg_events in (2, 4)):
+                torch.cuda.Event(enable_timing=True).record()
+        if self.timeline is not None and self.a.is_cuda and (self._tl_filter is None or label in self._tl_filter):
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             self.timeline.append((p, label, ev))
 
+    def _alloc_nccl_buffers(self):
+        if self._nccl_bufs:
+            return
+        multi = self.world > 1
+        self.send = self.be.empty(max(self.max_m, 1), self.db) if multi else None
+        self.gath = self.be.empty(self.world * max(self.max_m, 1), self.db) if multi else None
+        # panel in global row order, double buffered (look-ahead prepares panel p + 1 while panel p is in use)
+        self.pfull = [self.be.empty(self.n, self.db) for _ in range(2)] if multi else None
+        self._nccl_bufs = True
+
+    # ---- one panel, peer-store exchange (csrc/exchange.cu) ---------------------------------------------------
+    def _panel_peer(self, p, sums, info):
+        """Runs on the CURRENT stream.  Returns (ls, m, arows, pfull): this rank's rows below the diagonal block,
+        their solved panel part in local order (A operand of the update) and the whole panel in global order."""
+        lib, lay, n, db, P, px = self.be.lib, self.lay, self.n, self.db, self.world, self.px
+        s = self.be._s()
+        c0, c1 = p * db, min((p + 1) * db, n)
+        w = c1 - c0
+        owner = lay.owner(p)
+        seq = self.seq_base + p + 1
+        ck = self.be._ck
+        if self.rank == owner:
+            lo = lay.local_offset(p)
+            blk = self.a[lo:lo + w, c0:c1]
+            ck(lib.smnngp_stage_factor_diag_inv_f64(s, C.c_void_p(blk.data_ptr()), blk.stride(0), w,
+                                                    C.c_void_p(self.tdiag.data_ptr()), C.c_void_p(self.linv4.data_ptr()),
+                                                    C.c_void_p(sums.data_ptr()), C.c_void_p(info.data_ptr()), c0),
+               "factor_diag_inv")
+            ck(lib.smnngp_stage_scatter_inverse_f64(s, C.c_void_p(self.tdiag.data_ptr() + w * w * 8), w, w, px.w_ptrs,
+                                                    P, db, px.flag_ptrs, 0, seq,
+                                                    C.c_void_p(self.counters.data_ptr())), "scatter_inverse")
+        self._mark(p, "diag")
+        if not self.emulate or self.rank == owner:           # (dry-run: nobody else is there to raise flags)
+            ck(lib.smnngp_stage_wait_flags_f64(s, px.flags_local, 0, 1, seq, self.wait_timeout_s,
+                                               C.c_void_p(info.data_ptr())), "wait W")
+        self._mark(p, "bcast")
+        if self.rank == owner:
+            ls = lay.local_offset(p) + w
+            m = self.mloc - ls
+        else:
+            ls, m = lay.rows_from_block(p + 1)
+        ploc = self.ploc[p & 1]
+        slot = p % 3
+        r = self.a[ls:ls + max(m, 1), c0:c1]
+        ck(lib.smnngp_stage_trsm_scatter_f64(s, C.c_void_p(r.data_ptr()), r.stride(0), m, w,
+                                             C.c_void_p(px.w_local.data_ptr()), db, C.c_void_p(ploc.data_ptr()), db,
+                                             px.panel_ptrs[slot], P, self.rank, db, ls, c1, n, db, px.flag_ptrs,
+                                             8 + self.rank, seq, C.c_void_p(self.counters.data_ptr() + 16)),
+           "trsm_scatter")
+        self._mark(p, "trsm")
+        bn = n // db                                                   # block of the appended row y^T
+        if m > 0 and self.rank == lay.owner(bn):
+            lrow = lay.local_offset(bn) + (n - bn * db)
+            if lrow >= ls:
+                self.zvec[c0:c1].copy_(ploc[lrow - ls, :w])           # z = L^-1 y, one panel's worth
+        if c1 >= n:
+            return ls, m, None, None
+        first, count = (8 + self.rank, 1) if self.emulate else (8, P)
+        ck(lib.smnngp_stage_wait_flags_f64(s, px.flags_local, first, count, seq, self.wait_timeout_s,
+                                           C.c_void_p(info.data_ptr())), "wait panel")
+        self._mark(p, "gather")
+        return ls, m, ploc[:max(m, 1), :w], px.panel_local[slot][:n - c1, :w]
+
     # ---- one panel: diagonal block, broadcast, TRSM of the local rows, all-gather of the panel ---------------
     def _panel(self, p, sums, info, slot):
+        if self.px is not None:
+            return self._panel_peer(p, sums, info)
+        self._alloc_nccl_buffers()
+        ls, m, pfull = self._panel_nccl(p, sums, info, slot)
+        arows = self.a[ls:ls + max(m, 1), p * self.db:min((p + 1) * self.db, self.n)]
+        return ls, m, arows, pfull
+
+    def _panel_nccl(self, p, sums, info, slot):
         """Runs on the CURRENT stream.  Returns (ls, m, pfull): this rank's rows below the diagonal block and the
         whole panel for global rows [c1, N) in global order (None for the last panel)."""
         be, lay, n, db, P = self.be, self.lay, self.n, self.db, self.world
@@ -299,7 +459,7 @@ class DistributedLML:
             ev_panel.record(side)
         for p in range(npanels):
             c0, c1 = p * db, min((p + 1) * db, n)
-            ls, m, pfull = cur
+            ls, m, arows, pfull = cur
             if cuda:
                 main.wait_event(ev_panel)                                  # panel p is factored and gathered
             self._mark(p, "main_start")
@@ -310,7 +470,7 @@ class DistributedLML:
             shift = gb0 * db - c1
             na = min(db, n - c1)                                           # next panel's block column first
             if m > 0:
-                be.update(self.a[ls:ls + m, c0:c1], pfull[:na], self.a[ls:ls + m, c1:c1 + na], True, db, P, shift)
+                be.update(arows[:m], pfull[:na], self.a[ls:ls + m, c1:c1 + na], True, db, P, shift)
             self._mark(p, "update_a")
             if cuda:
                 ev_a = torch.cuda.Event()
@@ -325,7 +485,7 @@ class DistributedLML:
                 # leave SMs to the look-ahead chain only when it is long relative to this update (~1 ms of chain vs
                 # 5 % of the update): estimated update time at 33 TFLOP/s below 18 ms
                 t_est = 2.0 * m * (n - c1 - na) * w / 33e12
-                be.update(self.a[ls:ls + m, c0:c1], pfull[na:], self.a[ls:ls + m, c1 + na:n], True, db, P,
+                be.update(arows[:m], pfull[na:], self.a[ls:ls + m, c1 + na:n], True, db, P,
                           shift - na, self.sm_reserve if t_est < self.reserve_below_s else 0)
             self._mark(p, "update_b")
             cur = nxt
@@ -334,8 +494,13 @@ class DistributedLML:
         # z = (L^-1 y)^T sits in global row N on its owner
         bn = n // db
         if self.rank == lay.owner(bn):
-            lrow = lay.local_offset(bn) + (n - bn * db)
-            be.sumsq(self.a[lrow, :n], sums[1:2])
+            if self.px is not None:
+                be.sumsq(self.zvec, sums[1:2])
+            else:
+                lrow = lay.local_offset(bn) + (n - bn * db)
+                be.sumsq(self.a[lrow, :n], sums[1:2])
+        if self.px is not None:
+            self.seq_base += npanels + 1
         if P > 1 and not self.emulate:
             dist.all_reduce(sums, group=self.group)
             dist.all_reduce(info, op=dist.ReduceOp.MAX, group=self.group)

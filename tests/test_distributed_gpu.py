@@ -37,7 +37,7 @@ def test_single_rank_stage_path_matches_oracle_and_fused(n, db):
     assert abs(out[1].item() - fused[1].item()) <= 1e-12 * abs(ref)
 
 
-def _worker(rank, world, port, n, d, db, q):
+def _worker(rank, world, port, n, d, db, q, exchange="auto"):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -51,22 +51,28 @@ def _worker(rank, world, port, n, d, db, q):
         from tests.synth import regression_data, DEFAULT_HP as hp
         x, y, *_ = regression_data(n, d)
         dev = torch.device("cuda", rank)
-        solver = DistributedLML(n, d, sm.StackSpec(3, "relu", "mlp"), dev, block=db)
-        out, info = solver.lml(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), sm.make_hp(device=dev, **hp))
+        solver = DistributedLML(n, d, sm.StackSpec(3, "relu", "mlp"), dev, block=db, exchange=exchange)
+        assert solver.exchange == ("peer" if exchange == "auto" else exchange)
+        xd, yd, hpd = torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), sm.make_hp(device=dev, **hp)
+        out, info = solver.lml(xd, yd, hpd)
+        out2, _ = solver.lml(xd, yd, hpd)                    # second evaluation: buffers / sequence numbers reused
+        assert out2.cpu().tolist() == out.cpu().tolist()
         q.put((rank, out.cpu().tolist(), int(info.item())))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,db", [(1500, 128), (3000, 256)])
-def test_two_rank_nccl_matches_oracle(n, db):
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("n,db", [(1500, 128), (3000, 256), (2900, 512)])
+def test_two_rank_matches_oracle(n, db, exchange):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, 29700 + n % 100, n, 8, db, q)) for r in range(2)]
+    port = 29700 + n % 100 + (50 if exchange == "peer" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, 8, db, q, exchange)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(2)]
