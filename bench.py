@@ -292,7 +292,9 @@ def run_ours(args):
             "config": {"workload": f"C3 NNGP Gram+Cholesky+Student-t LML, N={n} D={d} L=3 relu, eps=1e-6 a=b=2",
                        "algorithmic_flops_per_step": flops,
                        "l2": "working set 8*N^2 B >> 126 MB L2 (inputs larger than L2, no explicit flush)",
-                       "parallelism": "1 GPU fused call" if world == 1 else f"block-row cyclic over {world} GPUs, NCCL"},
+                       "parallelism": "1 GPU fused call" if world == 1 else
+                       f"block-row cyclic over {world} GPUs, panel exchange: " +
+                       ("NVLink peer stores (CUDA IPC)" if solver.exchange == "peer" else "NCCL broadcast + all-gather")},
             "loss": loss, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -273,6 +273,7 @@ class DistributedLML:
         # the persistent update kernel otherwise occupies every SM until it ends
         self.sm_reserve = int(os.environ.get("SMNNGP_SM_RESERVE", "8" if self.world > 1 else "0"))
         self.reserve_below_s = float(os.environ.get("SMNNGP_RESERVE_BELOW_MS", "18")) * 1e-3
+        self.sm_reserve_auto = "SMNNGP_SM_RESERVE" not in os.environ
 
     # ---- stages ----------------------------------------------------------------------------------------------
     def _build_gram(self, x, y, hp):
@@ -485,8 +486,15 @@ class DistributedLML:
                 # leave SMs to the look-ahead chain only when it is long relative to this update (~1 ms of chain vs
                 # 5 % of the update): estimated update time at 33 TFLOP/s below 18 ms
                 t_est = 2.0 * m * (n - c1 - na) * w / 33e12
-                be.update(arows[:m], pfull[na:], self.a[ls:ls + m, c1 + na:n], True, db, P,
-                          shift - na, self.sm_reserve if t_est < self.reserve_below_s else 0)
+                if self.px is not None and self.sm_reserve_auto:
+                    # SMs the fused panel solve needs to keep pace with this update: solve flops m w^2 at ~0.2 TF/s
+                    # per SM against update flops 2 m ncols w at 33 TF/s -> 82.5 w / ncols, independent of m and P;
+                    # x4.5 margin (measured: remote stores + tile quantisation make the solve ~3x slower per SM than the
+                    # model, and the chain also holds the owner's diagonal block + the slowest rank) + 3
+                    reserve = min(32, max(2, int(4.5 * 82.5 * w / (n - c1 - na)) + 3))
+                else:
+                    reserve = self.sm_reserve if t_est < self.reserve_below_s else 0
+                be.update(arows[:m], pfull[na:], self.a[ls:ls + m, c1 + na:n], True, db, P, shift - na, reserve)
             self._mark(p, "update_b")
             cur = nxt
         if cuda:
