@@ -274,6 +274,30 @@ def run_ours(args):
                                "(smnngp_dmma_peak_tflops; MEASURED_PEAKS.json has no FP64 figure; "
                                "profiles/r01_fp64_peak.txt: 37.1 TF/s, cuBLAS Dgemm 36.0)"}
 
+    # ---- extra (not the headline): loss + gradient w.r.t. the six scalars, one call, same inputs ----
+    grad = None
+    if world == 1 and not args.no_grad:
+        try:
+            sm.device.release_workspaces()
+            torch.cuda.empty_cache()
+            sm.device.lml_grad(xd, yd, spec=spec, hp=hp_dev, kind="student_t")      # warm-up
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            og, gg, _ = sm.device.lml_grad(xd, yd, spec=spec, hp=hp_dev, kind="student_t")
+            g1.record()
+            torch.cuda.synchronize()
+            gms = g0.elapsed_time(g1)
+            gfl = float(n) ** 3 + 2.0 * n * (n + 1.0) * d       # N^3/3 x 3 (factor, inverse, SYRK) + two Gram passes
+            grad = {"ms_per_step": gms, "value": gfl / (gms * 1e-3) * 1e-12, "unit": UNIT,
+                    "algorithmic_flops_per_step": gfl, "loss": float(og[1].item()),
+                    "dloss_dhp": [float(v) for v in gg.cpu().tolist()],
+                    "api": "smnngp_lml_grad_f64 (spax.SPR.loss_and_grad)"}
+            sm.device.release_workspaces()
+            torch.cuda.empty_cache()
+        except Exception as e:                                   # e.g. not enough memory for 16 N^2 bytes
+            grad = {"error": repr(e)}
+
     # ---- CPU baseline: the oracle port on a bounded sample, rank 0, N = 1 only ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -296,7 +320,7 @@ def run_ours(args):
                        f"block-row cyclic over {world} GPUs, panel exchange: " +
                        ("NVLink peer stores (CUDA IPC)" if solver.exchange == "peer" else "NCCL broadcast + all-gather")},
             "loss": loss, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": cpu}
+            "cpu_baseline": cpu, "value_and_gradient": grad}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -311,6 +335,7 @@ def main():
     ap.add_argument("--rows", dest="n", type=int, default=60000, help="N (training points)")
     ap.add_argument("--features", dest="d", type=int, default=784, help="D (input features)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-grad", action="store_true", help="skip the extra value+gradient measurement (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

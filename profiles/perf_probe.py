@@ -46,6 +46,15 @@ if "gram" in which:
         t = timed(lambda: sm.device.gram(x, spec=spec, hp=hp, out=out))
         print(f"gram full(mirror) N={n} D={d} L=3: {t:9.3f} ms", flush=True)
         del x, out
+if "gram60k" in which:
+    n, d = 60000, 784
+    x = torch.from_numpy(pixel_data(n, d)[0]).cuda()
+    out = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    for L in (0, 1, 3):
+        sp = sm.StackSpec(L, "relu", "mlp")
+        t = timed(lambda: sm.device.gram(x, spec=sp, hp=hp, lower_only=True, out=out))
+        print(f"gram lower N={n} D={d} L={L}: {t:9.3f} ms  contraction {n*(n+1)*d/t*1e-9:7.2f} TFLOP/s  {L*n*(n+1)/2/t*1e-6:8.2f} Geval/s", flush=True)
+    del x, out
 if "lml" in which:
     for (n, d) in ((10000, 8), (30000, 784), (60000, 784)):
         xs, ys, *_ = pixel_data(n, d) if d > 100 else regression_data(n, d)[:2] + (None,)

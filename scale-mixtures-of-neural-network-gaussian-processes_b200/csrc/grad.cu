@@ -149,61 +149,71 @@ __device__ __forceinline__ void grad_epilogue(const GradParams& p, double (&acc)
       al_c[ni][e] = p.alpha[cc[ni][e]];
     }
 
-#pragma unroll
-  for (int mi = 0; mi < MI; mi++) {
-    const int r = rbase + mi * 8;
-    if (r >= N || cbase > r) continue;
-    double k[NI][2], dw[NI][2], db[NI][2];
-#pragma unroll
-    for (int ni = 0; ni < NI; ni++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const double k0 = acc[mi][ni][e] * inv_d;
-        // dense-resnet: leading Dense(512)
-        k[ni][e] = resnet ? fma(w2, k0, b2) : k0;
-        dw[ni][e] = resnet ? 2.0 * w * k0 : 0.0;
-        db[ni][e] = resnet ? 2.0 * b : 0.0;
-      }
-    for (int a = 0; a < n_act; a++) {
-      const double e1 = t0[a * tl + r], fw1 = t1[a * tl + r], fb1 = t2[a * tl + r];
-      const bool plain = !resnet || (a == n_act - 1);
+  // ROLLED over the 8 row groups (see gram_epilogue): each trip works on accumulator row 0 and rotates the rows
+  // through the registers - the fully unrolled version was ~29k instructions and ran at the instruction-fetch rate.
+#pragma unroll 1
+  for (int it = 0; it < MI; it++) {
+    const int r = rbase + it * 8;
+    if (r < N && cbase <= r) {
+      double k[NI][2], dw[NI][2], db[NI][2];
 #pragma unroll
       for (int ni = 0; ni < NI; ni++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-          const long long ci = a * tl + cc[ni][e];
-          const double e2 = t0[ci], fw = fw1 + t1[ci], fb = fb1 + t2[ci];
-          double kin = k[ni][e], dwin = dw[ni][e], dbin = db[ni][e];
-          if (!resnet) {                                         // Dense(512, W_std, b_std)
-            dwin = fma(w2, dwin, 2.0 * w * kin);
-            dbin = fma(w2, dbin, 2.0 * b);
-            kin = fma(w2, kin, b2);
+          const double k0 = acc[0][ni][e] * inv_d;
+          // dense-resnet: leading Dense(512)
+          k[ni][e] = resnet ? fma(w2, k0, b2) : k0;
+          dw[ni][e] = resnet ? 2.0 * w * k0 : 0.0;
+          db[ni][e] = resnet ? 2.0 * b : 0.0;
+        }
+      for (int a = 0; a < n_act; a++) {
+        const double e1 = t0[a * tl + r], fw1 = t1[a * tl + r], fb1 = t2[a * tl + r];
+        const bool plain = !resnet || (a == n_act - 1);
+#pragma unroll
+        for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const long long ci = a * tl + cc[ni][e];
+            const double e2 = t0[ci], fw = fw1 + t1[ci], fb = fb1 + t2[ci];
+            double kin = k[ni][e], dwin = dw[ni][e], dbin = db[ni][e];
+            if (!resnet) {                                         // Dense(512, W_std, b_std)
+              dwin = fma(w2, dwin, 2.0 * w * kin);
+              dbin = fma(w2, dbin, 2.0 * b);
+              kin = fma(w2, kin, b2);
+            }
+            double ph, phw, phb;
+            phi_dual<ACT>(kin, dwin, dbin, e1, e2, fw, fb, ph, phw, phb);
+            if (plain) {
+              k[ni][e] = ph; dw[ni][e] = phw; db[ni][e] = phb;
+            } else {                                               // ResBlock: z + Dense(act(z))
+              k[ni][e] = kin + fma(w2, ph, b2);
+              dw[ni][e] = dwin + fma(w2, phw, 2.0 * w * ph);
+              db[ni][e] = dbin + fma(w2, phb, 2.0 * b);
+            }
           }
-          double ph, phw, phb;
-          phi_dual<ACT>(kin, dwin, dbin, e1, e2, fw, fb, ph, phw, phb);
-          if (plain) {
-            k[ni][e] = ph; dw[ni][e] = phw; db[ni][e] = phb;
-          } else {                                               // ResBlock: z + Dense(act(z))
-            k[ni][e] = kin + fma(w2, ph, b2);
-            dw[ni][e] = dwin + fma(w2, phw, 2.0 * w * ph);
-            db[ni][e] = dbin + fma(w2, phb, 2.0 * b);
-          }
+      }
+      const double al_r = p.alpha[r];
+      const double* __restrict__ wrow = p.Winv + (long long)r * p.ldw;
+#pragma unroll
+      for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = cbase + ni * 8 + e;
+          if (c > r) continue;                                     // c <= r < N
+          double g = 0.5 * fma(gamma * al_r, al_c[ni][e], -wrow[c]);
+          if (c == r) sums[3] += g;
+          else g += g;                                             // the mirrored entry
+          sums[0] = fma(g, v2 * dw[ni][e], sums[0]);
+          sums[1] = fma(g, v2 * db[ni][e], sums[1]);
+          sums[2] = fma(g, k[ni][e], sums[2]);                     // d K / d last_w_std = 2 v k
         }
     }
-    const double al_r = p.alpha[r];
-    const double* __restrict__ wrow = p.Winv + (long long)r * p.ldw;
 #pragma unroll
-    for (int ni = 0; ni < NI; ni++)
+    for (int mi = 0; mi < MI - 1; mi++)
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int c = cbase + ni * 8 + e;
-        if (c > r) continue;                                     // c <= r < N
-        double g = 0.5 * fma(gamma * al_r, al_c[ni][e], -wrow[c]);
-        if (c == r) sums[3] += g;
-        else g += g;                                             // the mirrored entry
-        sums[0] = fma(g, v2 * dw[ni][e], sums[0]);
-        sums[1] = fma(g, v2 * db[ni][e], sums[1]);
-        sums[2] = fma(g, k[ni][e], sums[2]);                     // d K / d last_w_std = 2 v k
+      for (int ni = 0; ni < NI; ni++) {
+        acc[mi][ni][0] = acc[mi + 1][ni][0];
+        acc[mi][ni][1] = acc[mi + 1][ni][1];
       }
   }
   sums[2] *= 2.0 * v;

@@ -72,7 +72,7 @@ __global__ void scalars_kernel(const double* __restrict__ qfin, int N, const dou
 template <int ACT>
 __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)[MI][NI][2], int rbase, int cbase) {
   const double w2 = p.hp[HP_W] * p.hp[HP_W], b2 = p.hp[HP_B] * p.hp[HP_B], v2 = p.hp[HP_V] * p.hp[HP_V];
-  const double dD = (double)p.D;
+  const double inv_d = 1.0 / (double)p.D;
   const bool resnet = p.arch == ARCH_RESNET;
 
   // which of this thread's 64 entries are real output (edge tiles, strict upper part on the symmetric path)
@@ -86,7 +86,7 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)
         int r = rbase + mi * 8, c = cbase + ni * 8 + e;
         bool ok = r < p.N && c < p.M && (!p.symmetric || c <= r);
         if (ok) live |= 1ull << (mi * 8 + ni * 2 + e);
-        double k = acc[mi][ni][e] / dD;                 // kernel_fn normalises X.X'^T by the feature count
+        double k = acc[mi][ni][e] * inv_d;              // kernel_fn normalises X.X'^T by the feature count
         acc[mi][ni][e] = resnet ? (w2 * k + b2) : k;    // dense-resnet: leading Dense(512)
       }
 
@@ -106,32 +106,42 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)
         tc[ni][e] = c < p.M ? p.tab2[a * p.tab_ld2 + c] : 1.0;
       }
     const bool plain = !resnet || (a == n_act - 1);     // MLP layer, or the trailing activation of the resnet
-    if (live == ~0ull) {                                // interior tile: straight-line code, 64 independent chains
-#pragma unroll
-      for (int mi = 0; mi < MI; mi++)
+    {
+      // Entries that are not real output (edge tiles: zero accumulators and table value 1; strict upper part on the
+      // symmetric path) are evaluated like the others and simply never stored.
+      // The loop over the 8 row groups is ROLLED: each trip evaluates the 8 entries of accumulator
+      // row 0 (8 independent chains) and then rotates the rows through the registers, so the body is ~1/8 of the
+      // fully unrolled code.  Unrolled, the 64 inlined evaluations were ~90 KB of SASS per pass - more than the
+      // instruction cache holds next to the other math group - and the epilogue ran at the instruction-fetch rate
+      // (first layer of a tile ~4x slower than the FP64 pipe allows).
+#pragma unroll 1
+      for (int it = 0; it < MI; it++) {
+        double res[NI][2];
 #pragma unroll
         for (int ni = 0; ni < NI; ni++)
 #pragma unroll
           for (int e = 0; e < 2; e++) {
-            double k = acc[mi][ni][e];
+            double k = acc[0][ni][e];
             if (!resnet) k = w2 * k + b2;
-            const double ph = phi<ACT>(k, tr[mi], tc[ni][e]);
-            acc[mi][ni][e] = plain ? ph : k + (w2 * ph + b2);
+            const double ph = phi<ACT>(k, tr[0], tc[ni][e]);
+            res[ni][e] = plain ? ph : k + (w2 * ph + b2);
           }
-      continue;
-    }
 #pragma unroll
-    for (int mi = 0; mi < MI; mi++)
+        for (int mi = 0; mi < MI - 1; mi++) {
+          tr[mi] = tr[mi + 1];
 #pragma unroll
-      for (int ni = 0; ni < NI; ni++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          if (!((live >> (mi * 8 + ni * 2 + e)) & 1ull)) continue;
-          double k = acc[mi][ni][e];
-          if (!resnet) k = w2 * k + b2;                 // Dense(512, W_std, b_std)
-          double ph = phi<ACT>(k, tr[mi], tc[ni][e]);
-          acc[mi][ni][e] = plain ? ph : k + (w2 * ph + b2);  // ResBlock: z + Dense(act(z))
+          for (int ni = 0; ni < NI; ni++) {
+            acc[mi][ni][0] = acc[mi + 1][ni][0];
+            acc[mi][ni][1] = acc[mi + 1][ni][1];
+          }
         }
+#pragma unroll
+        for (int ni = 0; ni < NI; ni++) {
+          acc[MI - 1][ni][0] = res[ni][0];
+          acc[MI - 1][ni][1] = res[ni][1];
+        }
+      }
+    }
   }
 
   const double sh = (p.symmetric && p.shift != SHIFT_NONE) ? p.scal[SC_SHIFT0 + p.shift] : 0.0;
