@@ -222,6 +222,10 @@ void smnngp_set_tile_variant(int v);
  * high-priority side stream while the bulk of the trailing update runs (fork / join with events: still
  * enqueue-only and graph-capturable); 0 = single stream */
 void smnngp_set_lookahead(int on);
+/* tuning knob: SMs the bulk trailing update leaves free for the look-ahead chain (the persistent update kernel
+ * would otherwise hold every SM until it ends): trailing matrix narrower than 24000 columns / wider.  Default 8, 0
+ * (measured at C3: reserving even 1 SM costs more than the exposed diagonal-block chain, 2234 vs 2224 ms) */
+void smnngp_set_lookahead_reserve(int small_trailing, int large_trailing);
 /* diagnostic: device buffer (>= 64 int64) receiving clock64() at the phase boundaries of the diagonal-block
  * kernel; NULL switches it off */
 void smnngp_debug_potf2_clocks(long long* dev_buf);

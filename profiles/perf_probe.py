@@ -21,6 +21,9 @@ which = sys.argv[1:] or ["potrf", "gram", "lml"]
 sm._lib.load().smnngp_set_tile_variant(int(os.environ.get("TILE", "0")))
 sm._lib.load().smnngp_set_lookahead(int(os.environ.get("LOOKAHEAD", "1")))
 nbs = [int(v) for v in os.environ.get("NBS", "0").split(",")]
+if "RESERVE" in os.environ:
+    a_, b_ = (int(v) for v in os.environ["RESERVE"].split(","))
+    sm._lib.load().smnngp_set_lookahead_reserve(a_, b_)
 if "potrf" in which:
     for n in (8192, 16384, 32768):
         a = torch.zeros((n, n), dtype=torch.float64, device="cuda")

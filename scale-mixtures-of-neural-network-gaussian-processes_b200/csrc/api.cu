@@ -150,6 +150,10 @@ void smnngp_set_panel_width(int nb) { g_panel_width = nb > 0 ? (nb + PB - 1) / P
 void smnngp_set_tile_variant(int v) { tile_variant() = (v >= 0 && v <= 2) ? v : 0; }
 int smnngp_debug_occupancy(int variant) { return debug_gemm_occupancy(variant); }
 void smnngp_set_lookahead(int on) { lookahead_mode() = on ? 1 : 0; }
+void smnngp_set_lookahead_reserve(int small_trailing, int large_trailing) {
+  lookahead_reserve()[0] = small_trailing < 0 ? 0 : small_trailing;
+  lookahead_reserve()[1] = large_trailing < 0 ? 0 : large_trailing;
+}
 void smnngp_debug_potf2_clocks(long long* dev_buf) { potf2_clock_buffer() = dev_buf; }
 
 // ---- instrumentation for bench.py ------------------------------------------------------------------------

@@ -599,6 +599,11 @@ int& lookahead_mode() {
   static int v = 1;
   return v;
 }
+// SMs the bulk update leaves to the look-ahead chain: [0] trailing matrix < 24000 columns, [1] larger
+int* lookahead_reserve() {
+  static int v[2] = {8, 0};
+  return v;
+}
 
 cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long Mfull, long long N, int NB,
                             double* Linv_base, double* logdet, int* info, long long linv_stride,
@@ -649,32 +654,39 @@ cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long 
       }
     }
     if (c1 >= N) break;
-    const long long na = (c1 + NB < N) ? NB : N - c1;       // next panel's block column first
-    if (instr().time_updates) {
-      const double nsq = (double)(N - c1), extra = (double)(Mtot - N);
-      instr_begin_update(s, (nsq * (nsq + 1.0) + 2.0 * extra * nsq) * (double)w);
-    }
+    // Look-ahead split: the NEXT diagonal block (na x na, lower) is updated first, on the side stream, so that its
+    // factorisation chain can start at once; everything else - including the rest of the next block column - is one
+    // well-filled launch on the main stream that leaves a few SMs to the chain when the trailing matrix is small.
+    const long long na = (c1 + NB < N) ? NB : N - c1;
+    LA_CK(cudaEventRecord(la->ev_a, s));                    // panel p solved (TRSM done on the main stream)
+    LA_CK(cudaStreamWaitEvent(la->side, la->ev_a, 0));
     {
       GemmParams u{};
       u.A = A + c1 * lda + c0; u.lda = lda;
       u.B = A + c1 * lda + c0; u.ldb = lda;
       u.C = A + c1 * lda + c1; u.ldc = lda;
-      u.M = (int)(Mtot - c1); u.N = (int)na; u.K = w; u.lower = 1;
-      LA_CK(launch_gemm_sub(s, u));
+      u.M = (int)na; u.N = (int)na; u.K = w; u.lower = 1;
+      LA_CK(launch_gemm_sub(la->side, u));
     }
-    LA_CK(cudaEventRecord(la->ev_a, s));
-    LA_CK(cudaStreamWaitEvent(la->side, la->ev_a, 0));
     const long long cb = c1 + na;
-    if (cb < N) {
+    if (cb < Mtot) {
+      // rows [cb, Mtot) x cols [c1, N): local row r may touch columns <= r + na (plain shifted diagonal = the
+      // block-row-cyclic mask with one huge block)
       GemmParams u{};
       u.A = A + cb * lda + c0; u.lda = lda;
-      u.B = A + cb * lda + c0; u.ldb = lda;
-      u.C = A + cb * lda + cb; u.ldc = lda;
-      u.M = (int)(Mtot - cb); u.N = (int)(N - cb); u.K = w; u.lower = 1;
-      u.sm_reserve = (N - cb < 24000) ? 8 : 0;
+      u.B = A + c1 * lda + c0; u.ldb = lda;
+      u.C = A + cb * lda + c1; u.ldc = lda;
+      u.M = (int)(Mtot - cb); u.N = (int)(N - c1); u.K = w; u.lower = 1;
+      u.cyc_db = 1 << 30; u.cyc_p = 1; u.base_shift = (int)na;
+      u.sm_reserve = lookahead_reserve()[(N - cb < 24000) ? 0 : 1];
+      if (instr().time_updates) {
+        const double nb = (double)(N > cb ? N - cb : 0), extra = (double)(Mtot - (N > cb ? N : cb));
+        const double pairs = 0.5 * nb * (nb + 1.0) + nb * (double)na + extra * (double)(N - c1);
+        instr_begin_update(s, 2.0 * pairs * (double)w);
+      }
       LA_CK(launch_gemm_sub(s, u));
+      if (instr().time_updates) instr_end_update(s);
     }
-    if (instr().time_updates) instr_end_update(s);
   }
 #undef LA_CK
   return cudaSuccess;

@@ -68,6 +68,11 @@ __global__ void scalars_kernel(const double* __restrict__ qfin, int N, const dou
   }
 }
 
+#ifndef SMNNGP_GRAM_RU
+#define SMNNGP_GRAM_RU 1
+#endif
+constexpr int RU = SMNNGP_GRAM_RU;   // accumulator rows (of 8 entries) evaluated per trip of the rolled epilogue loop
+
 // L-layer recursion + final Dense + diagonal shift + store for one warp's 64 x 32 part of a tile
 template <int ACT>
 __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)[MI][NI][2], int rbase, int cbase) {
@@ -115,31 +120,35 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)
       // instruction cache holds next to the other math group - and the epilogue ran at the instruction-fetch rate
       // (first layer of a tile ~4x slower than the FP64 pipe allows).
 #pragma unroll 1
-      for (int it = 0; it < MI; it++) {
-        double res[NI][2];
+      for (int it = 0; it < MI / RU; it++) {
+        double res[RU][NI][2];
 #pragma unroll
-        for (int ni = 0; ni < NI; ni++)
+        for (int u = 0; u < RU; u++)
 #pragma unroll
-          for (int e = 0; e < 2; e++) {
-            double k = acc[0][ni][e];
-            if (!resnet) k = w2 * k + b2;
-            const double ph = phi<ACT>(k, tr[0], tc[ni][e]);
-            res[ni][e] = plain ? ph : k + (w2 * ph + b2);
-          }
+          for (int ni = 0; ni < NI; ni++)
 #pragma unroll
-        for (int mi = 0; mi < MI - 1; mi++) {
-          tr[mi] = tr[mi + 1];
+            for (int e = 0; e < 2; e++) {
+              double k = acc[u][ni][e];
+              if (!resnet) k = w2 * k + b2;
+              const double ph = phi<ACT>(k, tr[u], tc[ni][e]);
+              res[u][ni][e] = plain ? ph : k + (w2 * ph + b2);
+            }
+#pragma unroll
+        for (int mi = 0; mi < MI - RU; mi++) {
+          tr[mi] = tr[mi + RU];
 #pragma unroll
           for (int ni = 0; ni < NI; ni++) {
-            acc[mi][ni][0] = acc[mi + 1][ni][0];
-            acc[mi][ni][1] = acc[mi + 1][ni][1];
+            acc[mi][ni][0] = acc[mi + RU][ni][0];
+            acc[mi][ni][1] = acc[mi + RU][ni][1];
           }
         }
 #pragma unroll
-        for (int ni = 0; ni < NI; ni++) {
-          acc[MI - 1][ni][0] = res[ni][0];
-          acc[MI - 1][ni][1] = res[ni][1];
-        }
+        for (int u = 0; u < RU; u++)
+#pragma unroll
+          for (int ni = 0; ni < NI; ni++) {
+            acc[MI - RU + u][ni][0] = res[u][ni][0];
+            acc[MI - RU + u][ni][1] = res[u][ni][1];
+          }
       }
     }
   }

@@ -13,6 +13,7 @@ int& tile_variant();
 int debug_gemm_occupancy(int variant);
 // 1 (default): the fused factorisation runs the next panel's diagonal block on a side stream (look-ahead)
 int& lookahead_mode();
+int* lookahead_reserve();
 // diagnostic: when non-null, thread 0 of the diagonal-block kernel stores clock64() at its phase boundaries
 long long*& potf2_clock_buffer();
 

@@ -233,7 +233,6 @@ class DistributedLML:
             self.world = dist.get_world_size(group) if dist.is_initialized() else 1
             self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.timeline = None          # list of (panel, label, event) when profiling is switched on
-        self._dbg_events = int(os.environ.get("SMNNGP_MAIN_EVENTS", "0"))
         self._tl_filter = None
         self._gidx = {}
         self.db = int(block) if block else default_block(self.n, self.world)
@@ -307,9 +306,6 @@ class DistributedLML:
         return idx
 
     def _mark(self, p, label):
-        if self._dbg_events and self.a.is_cuda:
-            if (label == "update_a" and self._dbg_events in (2, 3)) or (label == "update_b" and self._dbg_events in (2, 4)):
-                torch.cuda.Event(enable_timing=True).record()
         if self.timeline is not None and self.a.is_cuda and (self._tl_filter is None or label in self._tl_filter):
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()

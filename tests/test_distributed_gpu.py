@@ -82,3 +82,23 @@ def test_two_rank_matches_oracle(n, db, exchange):
     ref = _ref(n, 8, "student_t")
     for rank, out, info in res:
         assert info == 0 and abs(out[1] - ref) <= 1e-8 * abs(ref)
+
+
+def test_emulated_rank_schedule_runs_on_one_gpu():
+    """DistributedLML(emulate=(P, rank)): the timing dry-run of one rank of a P-rank job (peer-store exchange with
+    every peer aliased to the local buffers) must run to completion and record a timeline; its numbers are not
+    meaningful, only its launches are."""
+    import torch
+    import smnngp_b200 as sm
+    from smnngp_b200.distributed import DistributedLML
+    from tests.synth import regression_data, DEFAULT_HP as hp
+    n, d = 3000, 8
+    x, y, *_ = regression_data(n, d)
+    job = DistributedLML(n, d, sm.StackSpec(3, "relu", "mlp"), "cuda", block=256, emulate=(4, 1))
+    assert job.exchange == "peer" and job.world == 4 and job.rank == 1
+    job.timeline = []
+    job.lml(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), sm.make_hp(**hp))
+    torch.cuda.synchronize()
+    labels = {lab for _, lab, _ in job.timeline}
+    assert {"main_start", "update_a", "update_b", "diag", "trsm", "gather"} <= labels
+    job.px.close()
