@@ -27,7 +27,7 @@ __all__ = [
     "softplus", "softplus_inverse", "nngp_gram", "nngp_diag", "jitter", "multivariate_t_logpdf",
     "multivariate_normal_logpdf", "prior_logpdf", "spr_loss", "nt_predict", "student_t_logpdf",
     "normal_logpdf", "likelihood_logpdf", "spr_test_nll", "sample_f_iid_moments", "test_log_likelihood",
-    "get_correct_count", "nngp_gram_dual", "spr_loss_grad",
+    "get_correct_count", "nngp_gram_dual", "spr_loss_grad", "find_grid_point",
 ]
 
 ACTS = ("relu", "erf")
@@ -354,6 +354,19 @@ def nt_predict(x, y, x_test, eps=1e-6, *, kernel_kwargs, k_dd=None):
     mean = k_td @ sla.cho_solve(c, y, check_finite=False)
     cov = k_tt - k_td @ sla.cho_solve(c, k_td.T, check_finite=False)
     return mean, cov
+
+
+def find_grid_point(x, y, x_test, eps, *, kernel_kwargs):
+    """One (w_std, b_std, eps) point of experiments/regression/find.py:134-160: predict(eps) (relative regulariser,
+    :75-77) -> (mean [T], diag cov [T]); log det(K + eps I) and y^T (K + eps I)^-1 y with the ABSOLUTE jitter
+    (:149-156; the reference forms the explicit inverse, the value is the same)."""
+    n = x.shape[0]
+    k_dd = nngp_gram(x, **kernel_kwargs)
+    mean, cov = nt_predict(x, y, x_test, eps, kernel_kwargs=kernel_kwargs, k_dd=k_dd)
+    a = k_dd + eps * np.eye(n)
+    sign, logdet = np.linalg.slogdet(a)
+    quad = float(y @ np.linalg.solve(a, y))
+    return mean.ravel(), np.diag(cov).copy(), float(logdet), quad
 
 
 def _t_logpdf(x, df, loc, scale):

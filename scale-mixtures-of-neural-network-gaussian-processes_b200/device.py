@@ -359,6 +359,20 @@ def test_nll(x, y, x_test, y_test, y_mean, y_std, *, spec: StackSpec, hp, kind="
     return nll[0], mean, var, info
 
 
+def grid_point(x, y, x_test, *, spec: StackSpec, hp):
+    """The device work of ONE point (w_std, b_std, eps) of the reference's grid search
+    (experiments/regression/find.py:134-160): the predictive with the RELATIVE regulariser (``predict(eps)``,
+    find.py:75-77) and, for the absolute one, ``log det(K + eps I)`` and ``y^T (K + eps I)^-1 y``
+    (find.py:149-156, there through an explicit inverse and ``multivariate_normal.logpdf``).  The (alpha, beta)
+    importance-sampling table that follows (find.py:163-186) is host arithmetic on these outputs.
+    Returns (mean [T], var [T], logdet, quad, info) with logdet = log det(K + eps I)."""
+    mean, var, info1 = predict(x, y, x_test, spec=spec, hp=hp, shift="eps_rel")
+    out, info2 = lml(x, y, spec=spec, hp=hp, kind="gauss")
+    if isinstance(x, np.ndarray):
+        return mean[:, 0], var, 2.0 * float(out[2]), float(out[3]), max(int(info1), int(info2))
+    return mean[:, 0], var, 2.0 * out[2], out[3], torch.maximum(info1, info2)
+
+
 def set_panel_width(nb: int):
     _lib.load().smnngp_set_panel_width(int(nb))
 

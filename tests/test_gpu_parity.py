@@ -356,3 +356,21 @@ def test_draw_stage(sm, kind):
     prior = InverseGammaPrior(a, b) if kind == "student_t" else GaussianPrior()
     f2 = prior.sample_f_iid(1234, md.T.contiguous(), vd, S).cpu().numpy()
     assert np.array_equal(f2, f)
+
+
+def test_find_grid_point(sm):
+    """experiments/regression/find.py:134-160, one (w_std, b_std, eps) point: predictive (relative regulariser) +
+    log det / quadratic form (absolute jitter)."""
+    import torch
+    x, y, xt, yt, *_ = regression_data(404, 13, t=52)
+    hp, hpd = _hp(sm, w_std=1.5, b_std=0.2, eps=1e-3)
+    kw = _kw(hp, 3, "relu", "mlp")
+    mean_ref, var_ref, logdet_ref, quad_ref = orc.find_grid_point(x, y, xt, hp["eps"], kernel_kwargs=kw)
+    mean, var, logdet, quad, info = sm.device.grid_point(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(),
+                                                         torch.from_numpy(xt).cuda(), spec=sm.StackSpec(3, "relu", "mlp"),
+                                                         hp=hpd)
+    assert int(info.item()) == 0
+    assert np.abs(mean.cpu().numpy() - mean_ref).max() <= LML_TOL * np.abs(mean_ref).max()
+    assert np.abs(var.cpu().numpy() - var_ref).max() <= LML_TOL * np.abs(var_ref).max()
+    assert abs(logdet.item() - logdet_ref) <= LML_TOL * abs(logdet_ref)
+    assert abs(quad.item() - quad_ref) <= LML_TOL * abs(quad_ref)
