@@ -140,6 +140,10 @@ class CudaBackend:
         return out
 
 
+class PeerUnavailable(RuntimeError):
+    """raised on EVERY rank when the peer-memory exchange cannot be set up on some rank"""
+
+
 class _RawCuda:
     """torch view of a raw device pointer (``__cuda_array_interface__``)."""
 
@@ -162,15 +166,20 @@ class PeerExchange:
         self.slot_bytes = n * db * 8
         total = self.off_panel + 3 * self.slot_bytes
         ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
-        if lib.smnngp_peer_alloc(total, C.byref(ptr), handle) != 0:
-            raise RuntimeError("smnngp_peer_alloc failed: " + lib.smnngp_last_error().decode())
-        self.local = ptr.value
+        ok = lib.smnngp_peer_alloc(total, C.byref(ptr), handle) == 0
+        self.local = ptr.value if ok else 0
         self._opened = []
-        torch.as_tensor(_RawCuda(self.local + self.off_flags, (32,), "<i8"), device=device).zero_()
+        if ok:
+            torch.as_tensor(_RawCuda(self.local + self.off_flags, (32,), "<i8"), device=device).zero_()
         if emulate or world == 1:
+            if not ok:
+                raise RuntimeError("smnngp_peer_alloc failed: " + lib.smnngp_last_error().decode())
             self.bases = [self.local] * world
         else:
-            mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+            # every rank takes part in every collective below even if its own step failed, so that a failure on
+            # one rank (no memory, CUDA IPC not permitted in this container) is seen by ALL ranks, which then
+            # fall back to the NCCL exchange together instead of dead-locking
+            mine = torch.tensor(list(handle) if ok else [0] * 64, dtype=torch.uint8, device=device)
             allh = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(allh, mine, group=group)          # also orders the zeroing above before any peer store
             self.bases = []
@@ -179,12 +188,18 @@ class PeerExchange:
                     self.bases.append(self.local)
                     continue
                 q, hh = C.c_void_p(), (C.c_ubyte * 64)(*allh[r].cpu().tolist())
-                if lib.smnngp_peer_open(hh, C.byref(q)) != 0:
-                    raise RuntimeError(f"smnngp_peer_open(rank {r}) failed: CUDA IPC unavailable")
-                self._opened.append(q.value)
-                self.bases.append(q.value)
+                if ok and any(hh) and lib.smnngp_peer_open(hh, C.byref(q)) == 0:
+                    self._opened.append(q.value)
+                    self.bases.append(q.value)
+                else:
+                    ok = False
+                    self.bases.append(0)
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
             torch.cuda.synchronize(device)
-            dist.barrier(group=group)
+            if int(flag.item()) == 0:
+                self.close()
+                raise PeerUnavailable("CUDA IPC peer memory could not be set up on every rank")
         self.w_local = torch.as_tensor(_RawCuda(self.local + self.off_w, (db, db), "<f8"), device=device)
         self.panel_local = [torch.as_tensor(_RawCuda(self.local + self.off_panel + k * self.slot_bytes, (n, db), "<f8"),
                                             device=device) for k in range(3)]
@@ -256,8 +271,14 @@ class DistributedLML:
         self.exchange = exchange
         self.px = None
         if exchange == "peer":
-            self.px = PeerExchange(self.be.lib, self.a.device, self.world, self.rank, group, self.n, self.db,
-                                   emulate=self.emulate)
+            try:
+                self.px = PeerExchange(self.be.lib, self.a.device, self.world, self.rank, group, self.n, self.db,
+                                       emulate=self.emulate)
+            except PeerUnavailable as e:                  # collective decision: every rank lands here together
+                import warnings
+                warnings.warn(f"smnngp: {e}; using the NCCL panel exchange")
+                self.exchange = exchange = "nccl"
+        if exchange == "peer":
             self.tdiag = self.be.empty(2 * self.db * self.db)            # owner's factorisation scratch [2w, w]
             self.linv4 = self.be.empty(nblk * PB * PB)
             self.ploc = [self.be.empty(max(self.mloc, 1), self.db) for _ in range(2)]
@@ -273,6 +294,14 @@ class DistributedLML:
         self.sm_reserve = int(os.environ.get("SMNNGP_SM_RESERVE", "8" if self.world > 1 else "0"))
         self.reserve_below_s = float(os.environ.get("SMNNGP_RESERVE_BELOW_MS", "18")) * 1e-3
         self.sm_reserve_auto = "SMNNGP_SM_RESERVE" not in os.environ
+
+    def close(self):
+        """release the peer-visible buffers (CUDA IPC mappings + the local cudaMalloc region)"""
+        if self.px is not None:
+            if self.a.is_cuda:
+                torch.cuda.synchronize(self.a.device)
+            self.px.close()
+            self.px = None
 
     # ---- stages ----------------------------------------------------------------------------------------------
     def _build_gram(self, x, y, hp):

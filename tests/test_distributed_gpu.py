@@ -63,7 +63,7 @@ def _worker(rank, world, port, n, d, db, q, exchange="auto"):
 
 
 @pytest.mark.parametrize("exchange", ["peer", "nccl"])
-@pytest.mark.parametrize("n,db", [(1500, 128), (3000, 256), (2900, 512)])
+@pytest.mark.parametrize("n,db", [(1500, 128), (3000, 256), (2900, 512), (1501, 128)])
 def test_two_rank_matches_oracle(n, db, exchange):
     import torch
     import torch.multiprocessing as mp
