@@ -182,6 +182,12 @@ int smnngp_stage_scatter_inverse_f64(void* stream, const double* Ut, int64_t ldu
 int smnngp_stage_signal_f64(void* stream, void* const* flag_ptrs, int P, int64_t flag_index, uint64_t seq);
 int smnngp_stage_wait_flags_f64(void* stream, const void* flags_local, int64_t first, int count, uint64_t seq,
                                 double timeout_s, int* info_dev);
+/* copy-engine flavour of the all-gather: trsm_scatter is called with P = 1 (own buffers only), then push_panel copies
+ * the solved rows (whole distribution blocks, w == db) to every other rank's panel buffer with cudaMemcpy2DAsync over
+ * NVLink and raises this rank's flag everywhere */
+int smnngp_stage_push_panel_f64(void* stream, const double* Ploc, int64_t m, int64_t w, int64_t db, int P, int rank,
+                                int64_t local_row0, int64_t c1, int64_t n, void* const* peer_ptrs,
+                                void* const* flag_ptrs, int64_t flag_index, uint64_t seq);
 /* how wait_flags waits: 0 (default) = cuStreamWaitValue64 on the stream (no SM occupied, no timeout), 1 = one-thread
  * spin kernel with the timeout described above */
 void smnngp_set_peer_wait_mode(int mode);

@@ -31,6 +31,7 @@ EXPORTS = [
     "smnngp_stage_update_f64", "smnngp_stage_sumsq_f64", "smnngp_stage_lml_finalize_f64",
     "smnngp_stage_factor_diag_inv_f64", "smnngp_stage_scatter_inverse_f64", "smnngp_stage_signal_f64",
     "smnngp_stage_wait_flags_f64", "smnngp_stage_trsm_scatter_f64", "smnngp_set_peer_wait_mode",
+    "smnngp_stage_push_panel_f64",
     "smnngp_peer_alloc", "smnngp_peer_open", "smnngp_peer_close", "smnngp_peer_free",
     "smnngp_instr_reset", "smnngp_instr_launches", "smnngp_instr_updates", "smnngp_dmma_peak_tflops",
 ]
@@ -149,6 +150,8 @@ def _declare(lib):
     lib.smnngp_stage_wait_flags_f64.argtypes = [_vp, _vp, _i64, _i, _u64, _d, _vp]
     lib.smnngp_stage_trsm_scatter_f64.argtypes = [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i,
                                                   _i64, _i64, _i64, _i64, _i64, _vp, _i64, _u64, _vp]
+    lib.smnngp_stage_push_panel_f64.argtypes = [_vp, _vp, _i64, _i64, _i64, _i, _i, _i64, _i64, _i64, _vp, _vp, _i64,
+                                                _u64]
     lib.smnngp_set_peer_wait_mode.restype = None
     lib.smnngp_set_peer_wait_mode.argtypes = [_i]
     lib.smnngp_peer_alloc.argtypes = [_sz, _vp, _vp]

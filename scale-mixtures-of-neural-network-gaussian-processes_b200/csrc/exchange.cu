@@ -49,7 +49,8 @@ __device__ __forceinline__ void signal_if_last_cta(const PeerSignal& sg) {
   if (prev == gridDim.x - 1) {
     *sg.counter = 0u;                    // next launch on this stream starts from zero
     __threadfence_system();
-    for (int q = 0; q < sg.P; q++) st_release_sys(sg.flag[q], sg.seq);
+    for (int q = 0; q < sg.P; q++)
+      if (sg.flag[q] != nullptr) st_release_sys(sg.flag[q], sg.seq);
   }
 }
 
@@ -87,14 +88,14 @@ struct EpiScatterTma {
           if (remote) {
 #pragma unroll
             for (int q = 0; q < MAX_PEERS; q++)
-              if (q < p.P) *reinterpret_cast<double2*>(p.peer[q] + prow + c) = v;
+              if (q < p.P && p.peer[q] != nullptr) *reinterpret_cast<double2*>(p.peer[q] + prow + c) = v;
           }
         } else {                                                              // odd panel width: last column
           p.g.C[(long long)r * p.g.ldc + c] = v.x;
           if (remote) {
 #pragma unroll
             for (int q = 0; q < MAX_PEERS; q++)
-              if (q < p.P) p.peer[q][prow + c] = v.x;
+              if (q < p.P && p.peer[q] != nullptr) p.peer[q][prow + c] = v.x;
           }
         }
       }
@@ -143,7 +144,8 @@ __global__ void __launch_bounds__(256) transpose_scatter_kernel(const double* __
 
 __global__ void signal_kernel(PeerSignal sg) {
   __threadfence_system();
-  for (int q = 0; q < sg.P; q++) st_release_sys(sg.flag[q], sg.seq);
+  for (int q = 0; q < sg.P; q++)
+    if (sg.flag[q] != nullptr) st_release_sys(sg.flag[q], sg.seq);
 }
 
 // one thread: wait until flags[0 .. count) >= seq.  A peer that died must not hang this GPU: after `timeout_ns`
@@ -204,7 +206,8 @@ void fill_signal(PeerSignal& sg, void* const* flag_ptrs, int P, long long flag_i
   sg.seq = seq;
   sg.counter = counter;
   for (int q = 0; q < MAX_PEERS; q++)
-    sg.flag[q] = q < P ? static_cast<unsigned long long*>(flag_ptrs[q]) + flag_index : nullptr;
+    sg.flag[q] = (q < P && flag_ptrs[q] != nullptr) ? static_cast<unsigned long long*>(flag_ptrs[q]) + flag_index
+                                                    : nullptr;
 }
 
 }  // namespace
@@ -273,6 +276,43 @@ int smnngp_stage_wait_flags_f64(void* stream, const void* flags_local, int64_t f
                                     info_dev);
   instr().launches++;
   return cudaGetLastError() == cudaSuccess ? SMNNGP_OK : SMNNGP_ECUDA;
+}
+
+// Push this rank's solved panel rows (local order, whole distribution blocks of db rows, pitch db = contiguous
+// blocks) to their global position in every OTHER rank's panel buffer with the copy engines - no SM, full NVLink
+// rate (remote 16-byte stores issued from the few SMs the look-ahead chain owns reached < 100 GB/s) - then raise
+// this rank's flag on every rank.  Rows whose global index is >= n (the appended y^T row) stay local.
+int smnngp_stage_push_panel_f64(void* stream, const double* Ploc, int64_t m, int64_t w, int64_t db, int P, int rank,
+                                int64_t local_row0, int64_t c1, int64_t n, void* const* peer_ptrs,
+                                void* const* flag_ptrs, int64_t flag_index, uint64_t seq) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!peer_ptrs || !flag_ptrs || P < 1 || P > MAX_PEERS || m < 0 || w != db || db <= 0 || rank < 0 || rank >= P ||
+      (m > 0 && !Ploc) || local_row0 % db != 0)
+    return SMNNGP_EINVAL;
+  const size_t blk_bytes = (size_t)db * db * sizeof(double);
+  // local blocks lb0, lb0+1, ... <-> global blocks (lb * P + rank); keep only rows with global index < n
+  const int64_t lb0 = local_row0 / db;
+  int64_t full = 0, tail_rows = 0;
+  for (int64_t r = 0; r < m; r += db) {
+    const int64_t g0 = ((lb0 + r / db) * P + rank) * db;
+    const int64_t rows = (m - r < db) ? m - r : db;
+    const int64_t ok = (g0 + rows <= n) ? rows : (n > g0 ? n - g0 : 0);
+    if (ok == db) full++;
+    else { tail_rows = ok; break; }
+  }
+  for (int q = 0; q < P; q++) {
+    if (q == rank) continue;
+    char* dst0 = static_cast<char*>(peer_ptrs[q]) + (size_t)((lb0 * P + rank) * db - c1) * db * sizeof(double);
+    if (full > 0 &&
+        cudaMemcpy2DAsync(dst0, (size_t)P * blk_bytes, Ploc, blk_bytes, blk_bytes, (size_t)full, cudaMemcpyDeviceToDevice,
+                          s) != cudaSuccess)
+      return SMNNGP_ECUDA;
+    if (tail_rows > 0 &&
+        cudaMemcpyAsync(dst0 + (size_t)full * P * blk_bytes, reinterpret_cast<const char*>(Ploc) + (size_t)full * blk_bytes,
+                        (size_t)tail_rows * db * sizeof(double), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+      return SMNNGP_ECUDA;
+  }
+  return smnngp_stage_signal_f64(stream, flag_ptrs, P, flag_index, seq);
 }
 
 // 0 = cuStreamWaitValue64 (default), 1 = spin kernel with timeout

@@ -207,6 +207,12 @@ class PeerExchange:
         self.w_ptrs = self._arr(self.off_w)
         self.flag_ptrs = self._arr(self.off_flags)
         self.panel_ptrs = [self._arr(self.off_panel + k * self.slot_bytes) for k in range(3)]
+        # own-buffers-only views for the copy-engine flavour (the solve kernel then stores locally only)
+        # (a NULL entry = "skip this rank")
+        self.panel_ptrs_self = [(C.c_void_p * self.world)(*[(self.local + self.off_panel + k * self.slot_bytes)
+                                                            if r == self.rank else None for r in range(self.world)])
+                                for k in range(3)]
+        self.flag_ptrs_none = (C.c_void_p * self.world)(*[None] * self.world)
 
     def _arr(self, off):
         return (C.c_void_p * self.world)(*[b + off for b in self.bases])
@@ -287,6 +293,10 @@ class DistributedLML:
             self.seq_base = 0
             self.send = self.gath = self.pfull = None
             self.wait_timeout_s = float(os.environ.get("SMNNGP_PEER_TIMEOUT_S", "20"))
+            # "store": the solve's epilogue stores into every rank's buffer (default); "ce": the solve stores locally and
+            # the copy engines push whole blocks (cudaMemcpy2DAsync).  Measured equal at 4 GPUs (610 ms) and 338 vs
+            # 333 ms at 8 GPUs: the solve is bound by the math on its few reserved SMs, not by the remote stores.
+            self.push = os.environ.get("SMNNGP_PUSH", "store")
             self.be.lib.smnngp_set_peer_wait_mode(int(os.environ.get("SMNNGP_PEER_WAIT", "0")))
         self.side = torch.cuda.Stream(device=self.a.device, priority=-1) if self.a.is_cuda else None
         # SMs the bulk update leaves free so the look-ahead chain (diagonal block, TRSM, NCCL) really overlaps:
@@ -384,11 +394,22 @@ class DistributedLML:
         ploc = self.ploc[p & 1]
         slot = p % 3
         r = self.a[ls:ls + max(m, 1), c0:c1]
-        ck(lib.smnngp_stage_trsm_scatter_f64(s, C.c_void_p(r.data_ptr()), r.stride(0), m, w,
-                                             C.c_void_p(px.w_local.data_ptr()), db, C.c_void_p(ploc.data_ptr()), db,
-                                             px.panel_ptrs[slot], P, self.rank, db, ls, c1, n, db, px.flag_ptrs,
-                                             8 + self.rank, seq, C.c_void_p(self.counters.data_ptr() + 16)),
-           "trsm_scatter")
+        if self.push == "ce" and w == db and c1 < n and ls % db == 0:
+            # solve with local stores only (own panel buffer + local-order copy, no flag), then the copy engines
+            # push whole blocks to the other ranks and the flag follows in stream order
+            ck(lib.smnngp_stage_trsm_scatter_f64(s, C.c_void_p(r.data_ptr()), r.stride(0), m, w,
+                                                 C.c_void_p(px.w_local.data_ptr()), db, C.c_void_p(ploc.data_ptr()), db,
+                                                 px.panel_ptrs_self[slot], P, self.rank, db, ls, c1, n, db,
+                                                 px.flag_ptrs_none, 8 + self.rank, seq,
+                                                 C.c_void_p(self.counters.data_ptr() + 16)), "trsm (local)")
+            ck(lib.smnngp_stage_push_panel_f64(s, C.c_void_p(ploc.data_ptr()), m, w, db, P, self.rank, ls, c1, n,
+                                               px.panel_ptrs[slot], px.flag_ptrs, 8 + self.rank, seq), "push_panel")
+        else:
+            ck(lib.smnngp_stage_trsm_scatter_f64(s, C.c_void_p(r.data_ptr()), r.stride(0), m, w,
+                                                 C.c_void_p(px.w_local.data_ptr()), db, C.c_void_p(ploc.data_ptr()), db,
+                                                 px.panel_ptrs[slot], P, self.rank, db, ls, c1, n, db, px.flag_ptrs,
+                                                 8 + self.rank, seq, C.c_void_p(self.counters.data_ptr() + 16)),
+               "trsm_scatter")
         self._mark(p, "trsm")
         bn = n // db                                                   # block of the appended row y^T
         if m > 0 and self.rank == lay.owner(bn):

@@ -124,3 +124,53 @@ def test_wait_flags_times_out_instead_of_hanging(sm):
     finally:
         lib.smnngp_set_peer_wait_mode(0)
     assert int(info.item()) == 0x7fffffff
+
+
+@pytest.mark.parametrize("m,db,P,rank,ls", [(1300, 256, 3, 2, 256), (1024, 512, 2, 1, 512), (700, 128, 8, 5, 0), (0, 128, 2, 0, 128)])
+def test_push_panel_copy_engine_flavour(sm, m, db, P, rank, ls):
+    """solve with local stores only (NULL peer entries are skipped, no flag), then cudaMemcpy2DAsync of whole
+    distribution blocks to the 'other ranks' (here: one second buffer) at their global rows + flag."""
+    import torch
+    lib = sm._lib.load()
+    w = db
+    rng = np.random.default_rng(m + db)
+    b = rng.standard_normal((w, w + 8))
+    L = sla.cholesky(b @ b.T / (w + 8) + 1e-2 * np.eye(w), lower=True)
+    Winv = np.tril(np.linalg.inv(L))
+    R = rng.standard_normal((max(m, 1), w))
+    lr = ls + np.arange(m)
+    g = ((lr // db) * P + rank) * db + lr % db
+    c1 = (int(g.min()) // db) * db - db if m else 0
+    n = int(g.max()) if m else 10                                     # the last row plays the appended y^T row
+    rows_total = (int(g.max()) - c1 + 1) if m else 1
+    rd, wd = torch.from_numpy(np.ascontiguousarray(R)).cuda(), torch.from_numpy(np.ascontiguousarray(Winv)).cuda()
+    ploc = torch.full((max(m, 1), db), np.nan, dtype=torch.float64, device="cuda")
+    own = torch.full((rows_total, db), np.nan, dtype=torch.float64, device="cuda")
+    other = torch.full((rows_total, db), np.nan, dtype=torch.float64, device="cuda")
+    flags = torch.zeros(16, dtype=torch.int64, device="cuda")
+    counter = torch.zeros(4, dtype=torch.int32, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    self_only = (C.c_void_p * P)(*[own.data_ptr() if q == rank else None for q in range(P)])
+    none = (C.c_void_p * P)(*[None] * P)
+    everyone = (C.c_void_p * P)(*[own.data_ptr() if q == rank else other.data_ptr() for q in range(P)])
+    fl = (C.c_void_p * P)(*[flags.data_ptr()] * P)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.smnngp_stage_trsm_scatter_f64(s, _vp(rd), w, m, w, _vp(wd), w, _vp(ploc), db, self_only, P, rank, db, ls,
+                                             c1, n, db, none, 8 + rank, 9, _vp(counter)) == 0
+    torch.cuda.synchronize()
+    assert int(flags[8 + rank].item()) == 0                           # no flag from the solve itself
+    assert lib.smnngp_stage_push_panel_f64(s, _vp(ploc), m, w, db, P, rank, ls, c1, n, everyone, fl, 8 + rank, 9) == 0
+    assert lib.smnngp_stage_wait_flags_f64(s, _vp(flags), 8 + rank, 1, 9, 5.0, _vp(info)) == 0
+    torch.cuda.synchronize()
+    assert int(flags[8 + rank].item()) == 9
+    if m == 0:
+        return
+    want = sla.solve_triangular(L, R.T, lower=True).T
+    got = ploc.cpu().numpy()[:m, :w]
+    assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
+    o1, o2 = own.cpu().numpy(), other.cpu().numpy()
+    sent = g < n
+    assert np.array_equal(o1[g[sent] - c1], got[sent]) and np.array_equal(o2[g[sent] - c1], got[sent])
+    untouched = np.ones(rows_total, bool)
+    untouched[g[sent] - c1] = False
+    assert np.isnan(o1[untouched]).all() and np.isnan(o2[untouched]).all()
