@@ -122,6 +122,23 @@ int smnngp_test_nll_f64(void* stream, const double* X, const double* y, const do
                         double* nll_out_dev, double* mean_out, double* var_out, double* logp_out,
                         int* info_dev);
 
+/* ---- hyper-parameter grid search with a cached base Gram: the reference's
+ * experiments/regression/find.py:134-199 evaluates, for every (w_std, b_std) x eps of a grid, the kernel matrix
+ * (find.py:64-70), the predictive with the relative regulariser (find.py:73-78) and the log-determinant / quadratic
+ * form of K + eps I (find.py:149-156) on the SAME inputs.  X.X'^T does not depend on the scalars:
+ *   grid_base   K0dd [N, ld0] (lower) = X X^T / D, K0td [T, ld0t] = Xt X^T / D, q_d [N], q_t [T] = ||x||^2 / D   (once)
+ *   grid_point  one grid point from the bases: recursion-only passes (8 B read + 8 B written per entry) + the two
+ *               factorisations.  mean_out [T], var_out [T] (predict(eps), relative regulariser);
+ *               out_dev[2] = { sum log L_ii of chol(K + eps I)  (= 1/2 log det),  y^T (K + eps I)^-1 y }.
+ * The (alpha, beta) importance-sampling table that follows (find.py:163-186) is host arithmetic on these outputs. */
+int smnngp_grid_base_f64(void* stream, const double* X, const double* Xt, int64_t N, int64_t T, int64_t D,
+                         double* K0dd, int64_t ld0, double* K0td, int64_t ld0t, double* q_d, double* q_t);
+size_t smnngp_grid_workspace_bytes(int64_t N, int64_t T, int n_hidden, int arch);
+int smnngp_grid_point_f64(void* stream, const double* K0dd, int64_t ld0, const double* K0td, int64_t ld0t,
+                          const double* q_d, const double* q_t, const double* y, int64_t N, int64_t T, int n_hidden,
+                          int act, int arch, const double* hp_dev, void* workspace, size_t workspace_bytes,
+                          double* mean_out, double* var_out, double* out_dev, int* info_dev);
+
 /* ---- posterior draw stage of the classification / ensemble configuration.
  * mean [T, C]; var [T] (shared by the classes, var_per_class = 0) or [C, T] (var_per_class = 1); kind STUDENT_T:
  * InverseGammaPrior.sample_f_iid (spax/priors.py:60-68), f = mean + sqrt((b/a) var) t_{2a}; kind GAUSS:

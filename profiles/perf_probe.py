@@ -58,6 +58,15 @@ if "gram60k" in which:
         t = timed(lambda: sm.device.gram(x, spec=sp, hp=hp, lower_only=True, out=out))
         print(f"gram lower N={n} D={d} L={L}: {t:9.3f} ms  contraction {n*(n+1)*d/t*1e-9:7.2f} TFLOP/s  {L*n*(n+1)/2/t*1e-6:8.2f} Geval/s", flush=True)
     del x, out
+if "grid" in which:
+    for (n, t, d) in ((10000, 1000, 8), (10000, 1000, 784)):
+        xs, ys, xts, *_ = regression_data(n, d, t=t)
+        x, y, xt = torch.from_numpy(xs).cuda(), torch.from_numpy(ys).cuda(), torch.from_numpy(xts).cuda()
+        gs = sm.device.GridSearch(x, y, xt, spec=spec)
+        t_cached = timed(lambda: gs.point(hp))
+        t_scratch = timed(lambda: sm.device.grid_point(x, y, xt, spec=spec, hp=hp))
+        print(f"find.py grid point N={n} T={t} D={d}: cached base {t_cached:8.3f} ms, from scratch {t_scratch:8.3f} ms", flush=True)
+        del gs
 if "lml" in which:
     for (n, d) in ((10000, 8), (30000, 784), (60000, 784)):
         xs, ys, *_ = pixel_data(n, d) if d > 100 else regression_data(n, d)[:2] + (None,)

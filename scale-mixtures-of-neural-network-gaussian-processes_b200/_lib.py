@@ -27,6 +27,7 @@ EXPORTS = [
     "smnngp_test_nll_f64", "smnngp_lml_host_f64", "smnngp_predict_host_f64", "smnngp_test_nll_host_f64",
     "smnngp_host_release", "smnngp_set_panel_width", "smnngp_set_tile_variant", "smnngp_debug_occupancy", "smnngp_set_lookahead", "smnngp_set_lookahead_reserve", "smnngp_debug_potf2_clocks",
     "smnngp_sample_f_iid_f64", "smnngp_draw_metrics_f64",
+    "smnngp_grid_base_f64", "smnngp_grid_workspace_bytes", "smnngp_grid_point_f64",
     "smnngp_stage_qtable_f64", "smnngp_stage_gram_f64", "smnngp_stage_factor_diag_f64", "smnngp_stage_trsm_f64",
     "smnngp_stage_update_f64", "smnngp_stage_sumsq_f64", "smnngp_stage_lml_finalize_f64",
     "smnngp_stage_factor_diag_inv_f64", "smnngp_stage_scatter_inverse_f64", "smnngp_stage_signal_f64",
@@ -132,6 +133,11 @@ def _declare(lib):
     lib.smnngp_set_lookahead_reserve.argtypes = [_i, _i]
     lib.smnngp_set_lookahead.restype = None
     lib.smnngp_set_lookahead.argtypes = [_i]
+    lib.smnngp_grid_base_f64.argtypes = [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _vp]
+    lib.smnngp_grid_workspace_bytes.restype = _sz
+    lib.smnngp_grid_workspace_bytes.argtypes = [_i64, _i64, _i, _i]
+    lib.smnngp_grid_point_f64.argtypes = [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp,
+                                          _sz, _vp, _vp, _vp, _vp]
     lib.smnngp_sample_f_iid_f64.argtypes = [_vp, _vp, _vp, _i, _i64, _i64, _i64, _vp, _i, C.c_uint64, _vp]
     lib.smnngp_draw_metrics_f64.argtypes = [_vp, _vp, _vp, _i, _vp, _i64, _i64, _i64, _vp, _i, C.c_uint64, _vp, _vp, _vp]
     lib.smnngp_stage_qtable_f64.argtypes = [_vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp, _i64, _vp, _vp]

@@ -526,6 +526,76 @@ int smnngp_test_nll_f64(void* stream, const double* X, const double* y, const do
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// hyper-parameter grid search with a cached base Gram (experiments/regression/find.py)
+// ---------------------------------------------------------------------------------------------------------
+int smnngp_grid_base_f64(void* stream, const double* X, const double* Xt, int64_t N, int64_t T, int64_t D,
+                         double* K0dd, int64_t ld0, double* K0td, int64_t ld0t, double* q_d, double* q_t) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!X || !K0dd || !q_d || N <= 0 || D <= 0 || ld0 < N || T < 0 || (T > 0 && (!Xt || !K0td || !q_t || ld0t < N)) ||
+      N > INT32_MAX || T > INT32_MAX || D > INT32_MAX)
+    return fail(SMNNGP_EINVAL, "smnngp_grid_base_f64: invalid argument");
+  // unit scalars (hp = nullptr), no hidden layer: K0 = X X'^T / D and q0 = ||x||^2 / D
+  CU(launch_qtable(s, X, D, (int)N, (int)D, 0, ACT_RELU, ARCH_MLP, nullptr, nullptr, N, q_d));
+  CU(enqueue_sym_gram(s, X, N, D, 0, ACT_RELU, ARCH_MLP, nullptr, nullptr, nullptr, SHIFT_NONE, 0, K0dd, ld0));
+  if (T > 0) {
+    CU(launch_qtable(s, Xt, D, (int)T, (int)D, 0, ACT_RELU, ARCH_MLP, nullptr, nullptr, T, q_t));
+    CU(enqueue_cross_gram(s, Xt, T, X, N, D, 0, ACT_RELU, ARCH_MLP, nullptr, nullptr, nullptr, nullptr, K0td, ld0t));
+  }
+  return SMNNGP_OK;
+}
+
+size_t smnngp_grid_workspace_bytes(int64_t N, int64_t T, int n_hidden, int arch) {
+  Carver c(nullptr);
+  SolveWs w;
+  return carve_solve(c, w, N, T, 1, n_act_applications(n_hidden, arch));
+}
+
+int smnngp_grid_point_f64(void* stream, const double* K0dd, int64_t ld0, const double* K0td, int64_t ld0t,
+                          const double* q_d, const double* q_t, const double* y, int64_t N, int64_t T, int n_hidden,
+                          int act, int arch, const double* hp_dev, void* workspace, size_t workspace_bytes,
+                          double* mean_out, double* var_out, double* out_dev, int* info_dev) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!K0dd || !K0td || !q_d || !q_t || !y || !hp_dev || !mean_out || !var_out || !out_dev || !info_dev || N <= 0 ||
+      T <= 0 || ld0 < N || ld0t < N || !valid_stack(n_hidden, act, arch) || N + T + 1 > INT32_MAX)
+    return fail(SMNNGP_EINVAL, "smnngp_grid_point_f64: invalid argument");
+  Carver c(workspace);
+  SolveWs w;
+  if (carve_solve(c, w, N, T, 1, n_act_applications(n_hidden, arch)) > workspace_bytes || !workspace)
+    return fail(SMNNGP_EWORKSPACE, "smnngp_grid_point_f64: workspace too small");
+  CU(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
+  CU(launch_qtable_from_q(s, q_d, (int)N, n_hidden, act, arch, hp_dev, w.tab, N, w.q));
+  CU(launch_scalars(s, w.q, (int)N, hp_dev, w.scal));
+  CU(launch_qtable_from_q(s, q_t, (int)T, n_hidden, act, arch, hp_dev, w.tab_t, T, w.q_t));
+  GramParams g{};
+  g.N = (int)N; g.M = (int)N; g.tab1 = w.tab; g.tab2 = w.tab; g.tab_ld1 = N; g.tab_ld2 = N;
+  g.n_hidden = n_hidden; g.act = act; g.arch = arch; g.hp = hp_dev; g.scal = w.scal;
+  g.symmetric = 1; g.out_full = 0; g.K = w.A; g.ldk = w.lda;
+  // (1) predict(eps): K + eps tr(K)/N I, K_td rows and y^T carried through the factorisation (find.py:75-77, :139)
+  g.shift = SHIFT_EPS_REL;
+  CU(launch_gram_from_base(s, g, K0dd, ld0));
+  {
+    GramParams x = g;
+    x.N = (int)T; x.M = (int)N; x.tab1 = w.tab_t; x.tab_ld1 = T; x.shift = SHIFT_NONE; x.symmetric = 0; x.out_full = 1;
+    x.K = w.A + N * w.lda;
+    CU(launch_gram_from_base(s, x, K0td, ld0t));
+  }
+  CU(cudaMemcpyAsync(w.A + (N + T) * w.lda, y, N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  CU(potrf_trapezoid(s, w.A, w.lda, N + T + 1, N, pick_nb(N), w.linv, w.scal + SC_LOGDET, info_dev));
+  CU(launch_predict_finalize(s, w.A + N * w.lda, w.lda, w.A + (N + T) * w.lda, w.lda, w.q_t, (int)T, 1, N, info_dev,
+                             mean_out, var_out));
+  // (2) log det(K + eps I) and y^T (K + eps I)^-1 y with the ABSOLUTE jitter (find.py:149-156)
+  g.shift = SHIFT_EPS_ABS;
+  CU(launch_gram_from_base(s, g, K0dd, ld0));
+  CU(cudaMemcpyAsync(w.A + N * w.lda, y, N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemsetAsync(w.scal2, 0, SC_COUNT * sizeof(double), s));
+  CU(potrf_trapezoid(s, w.A, w.lda, N + 1, N, pick_nb(N), w.linv, w.scal2 + SC_LOGDET, info_dev));
+  CU(launch_sumsq(s, w.A + N * w.lda, N, w.scal2 + SC_QUAD));
+  CU(cudaMemcpyAsync(out_dev, w.scal2 + SC_LOGDET, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  CU(launch_fill_nan_if_bad(s, info_dev, out_dev, 2));
+  return SMNNGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host-buffer entry points
 // ---------------------------------------------------------------------------------------------------------
 void smnngp_host_release(void) {

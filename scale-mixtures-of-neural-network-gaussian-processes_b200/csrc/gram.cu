@@ -11,20 +11,12 @@ namespace smnngp {
 
 namespace {
 
-__global__ void qtable_kernel(const double* __restrict__ X, long long ldx, int N, int D, int n_hidden, int act,
-                              int arch, const double* __restrict__ hp, double* __restrict__ tab,
-                              long long tab_ld, double* __restrict__ qfin) {
-  int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  int lane = threadIdx.x & 31;
-  if (row >= N) return;
-  const double* x = X + (long long)row * ldx;
-  double s = 0.0;
-  for (int k = lane; k < D; k += 32) s = fma(x[k], x[k], s);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane != 0) return;
-  const double w2 = hp[HP_W] * hp[HP_W], b2 = hp[HP_B] * hp[HP_B], v2 = hp[HP_V] * hp[HP_V];
-  double q = s / (double)D;
+// per-row layer tables from the input variance q0 = ||x||^2 / D.  hp == nullptr: unit scalars (w = v = 1, b = 0)
+__device__ __forceinline__ void fill_row_tables(double q, int row, int n_hidden, int act, int arch,
+                                                const double* __restrict__ hp, double* __restrict__ tab,
+                                                long long tab_ld, double* __restrict__ qfin) {
+  const double w2 = hp ? hp[HP_W] * hp[HP_W] : 1.0, b2 = hp ? hp[HP_B] * hp[HP_B] : 0.0,
+               v2 = hp ? hp[HP_V] * hp[HP_V] : 1.0;
   if (arch == ARCH_MLP) {
     for (int a = 0; a < n_hidden; a++) {
       double u = w2 * q + b2;
@@ -41,6 +33,29 @@ __global__ void qtable_kernel(const double* __restrict__ X, long long ldx, int N
     q = act_diag(u, act);
   }
   qfin[row] = v2 * q;
+}
+
+__global__ void qtable_kernel(const double* __restrict__ X, long long ldx, int N, int D, int n_hidden, int act,
+                              int arch, const double* __restrict__ hp, double* __restrict__ tab,
+                              long long tab_ld, double* __restrict__ qfin) {
+  int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const double* x = X + (long long)row * ldx;
+  double s = 0.0;
+  for (int k = lane; k < D; k += 32) s = fma(x[k], x[k], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane != 0) return;
+  fill_row_tables(s / (double)D, row, n_hidden, act, arch, hp, tab, tab_ld, qfin);
+}
+
+// the same tables from a cached q0 (grid search: X is not touched again)
+__global__ void qtable_from_q_kernel(const double* __restrict__ q0, int N, int n_hidden, int act, int arch,
+                                     const double* __restrict__ hp, double* __restrict__ tab, long long tab_ld,
+                                     double* __restrict__ qfin) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row < N) fill_row_tables(q0[row], row, n_hidden, act, arch, hp, tab, tab_ld, qfin);
 }
 
 // single block, fixed reduction order (deterministic)
@@ -76,7 +91,9 @@ constexpr int RU = SMNNGP_GRAM_RU;   // accumulator rows (of 8 entries) evaluate
 // L-layer recursion + final Dense + diagonal shift + store for one warp's 64 x 32 part of a tile
 template <int ACT>
 __device__ __forceinline__ void gram_epilogue(const GramParams& p, double (&acc)[MI][NI][2], int rbase, int cbase) {
-  const double w2 = p.hp[HP_W] * p.hp[HP_W], b2 = p.hp[HP_B] * p.hp[HP_B], v2 = p.hp[HP_V] * p.hp[HP_V];
+  // hp == nullptr: unit scalars - the base Gram K0 = X.X'^T / D of the grid search (n_hidden = 0)
+  const double w2 = p.hp ? p.hp[HP_W] * p.hp[HP_W] : 1.0, b2 = p.hp ? p.hp[HP_B] * p.hp[HP_B] : 0.0,
+               v2 = p.hp ? p.hp[HP_V] * p.hp[HP_V] : 1.0;
   const double inv_d = 1.0 / (double)p.D;
   const bool resnet = p.arch == ARCH_RESNET;
 
@@ -199,6 +216,42 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS) gram_kernel(con
                      c0 + (warp % Cfg::WARPS_N) * 32 + (lane & 3) * 2);
 }
 
+// Recursion-only pass over a cached base Gram K0 (= X.X'^T / D): the hyper-parameter grid search of
+// experiments/regression/find.py:134-199 evaluates many (w_std, b_std) on the same inputs, so the contraction is done
+// once and every grid point is one HBM pass (8 B read + 8 B written per entry).  A 128 x 64 tile per CTA, the K0
+// values are loaded straight into the accumulator layout of the GEMM core and handed to the same epilogue.
+template <int ACT>
+__global__ void __launch_bounds__(128) gram_from_base_kernel(const GramParams p, const double* __restrict__ base,
+                                                             long long ldb) {
+  const int ntn = (p.M + 63) / 64;
+  int ti, tj;
+  decode_tile<2>(blockIdx.x, ntn, p.symmetric, ti, tj);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rbase = ti * 128 + (warp >> 1) * 64 + (lane >> 2), cbase = tj * 64 + (warp & 1) * 32 + (lane & 3) * 2;
+  const bool vec_ok = ((ldb & 1) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int mi = 0; mi < MI; mi++) {
+    const int r = rbase + mi * 8;
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++) {
+      const int c = cbase + ni * 8;
+      double2 v = make_double2(0.0, 0.0);
+      if (r < p.N && (!p.symmetric || c <= r)) {        // the strict upper part of a lower-only base is never read
+        const double* src = base + (long long)r * ldb + c;
+        if (c + 1 < p.M && vec_ok && (!p.symmetric || c + 1 <= r)) v = *reinterpret_cast<const double2*>(src);
+        else {
+          if (c < p.M) v.x = src[0];
+          if (c + 1 < p.M && (!p.symmetric || c + 1 <= r)) v.y = src[1];
+        }
+      }
+      acc[mi][ni][0] = v.x;
+      acc[mi][ni][1] = v.y;
+    }
+  }
+  gram_epilogue<ACT>(p, acc, rbase, cbase);
+}
+
 // TMA-fed persistent variant (tma_core.cuh)
 template <int ACT>
 struct EpiGramTma {
@@ -241,6 +294,25 @@ cudaError_t launch_qtable(cudaStream_t s, const double* X, long long ldx, int N,
   int warps_per_block = 8;
   unsigned blocks = (unsigned)((N + warps_per_block - 1) / warps_per_block);
   qtable_kernel<<<blocks, warps_per_block * 32, 0, s>>>(X, ldx, N, D, n_hidden, act, arch, hp, tab, tab_ld, qfin);
+  instr().launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_qtable_from_q(cudaStream_t s, const double* q0, int N, int n_hidden, int act, int arch,
+                                 const double* hp, double* tab, long long tab_ld, double* qfin) {
+  if (N <= 0) return cudaSuccess;
+  qtable_from_q_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(q0, N, n_hidden, act, arch, hp, tab, tab_ld, qfin);
+  instr().launches++;
+  return cudaGetLastError();
+}
+
+// p describes the OUTPUT (tables, hp, shift, symmetric, out_full, K, ldk; X1 / X2 / D are ignored)
+cudaError_t launch_gram_from_base(cudaStream_t s, GramParams p, const double* base, long long ldb) {
+  if (p.N <= 0 || p.M <= 0) return cudaSuccess;
+  p.D = 1;
+  const long long tiles = count_tiles<TilePair>(p.N, p.M, p.symmetric);
+  if (p.act == ACT_RELU) gram_from_base_kernel<ACT_RELU><<<(unsigned)tiles, 128, 0, s>>>(p, base, ldb);
+  else gram_from_base_kernel<ACT_ERF><<<(unsigned)tiles, 128, 0, s>>>(p, base, ldb);
   instr().launches++;
   return cudaGetLastError();
 }

@@ -62,6 +62,11 @@ __host__ __device__ __forceinline__ long long diag_limit(const GemmParams& p, in
 // per-row layer table + final marginal variance (nngp diag) for X [N, D]
 cudaError_t launch_qtable(cudaStream_t s, const double* X, long long ldx, int N, int D, int n_hidden, int act,
                           int arch, const double* hp, double* tab, long long tab_ld, double* qfin);
+// the same tables from cached input variances q0 [N] (hp == nullptr anywhere in this group: unit scalars)
+cudaError_t launch_qtable_from_q(cudaStream_t s, const double* q0, int N, int n_hidden, int act, int arch,
+                                 const double* hp, double* tab, long long tab_ld, double* qfin);
+// recursion-only pass over a cached base Gram (X.X'^T / D); p describes the output, X1 / X2 / D are ignored
+cudaError_t launch_gram_from_base(cudaStream_t s, GramParams p, const double* base, long long ldb);
 // scal[SC_TRMEAN], shift table; zeroes the log-det / quad accumulators
 cudaError_t launch_scalars(cudaStream_t s, const double* qfin, int N, const double* hp, double* scal);
 cudaError_t launch_gram(cudaStream_t s, const GramParams& p);

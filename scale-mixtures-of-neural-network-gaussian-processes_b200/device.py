@@ -373,6 +373,47 @@ def grid_point(x, y, x_test, *, spec: StackSpec, hp):
     return mean[:, 0], var, 2.0 * out[2], out[3], torch.maximum(info1, info2)
 
 
+class GridSearch:
+    """The reference's hyper-parameter grid search (experiments/regression/find.py:134-199) with the base Gram cached:
+    X.X^T / D, Xt.X^T / D and the input variances are computed once; every ``point(hp)`` is recursion-only passes over
+    the cached bases plus the two factorisations - the same outputs as ``grid_point`` without touching X again."""
+
+    def __init__(self, x, y, x_test, *, spec: StackSpec):
+        _require_cuda()
+        self.lib = _lib.load()
+        self.spec = spec
+        x = _f64(x)
+        self.y = _f64(y, x.device)
+        xt = _f64(x_test, x.device)
+        self.n, d = x.shape
+        self.t = xt.shape[0]
+        dev = x.device
+        self.ld0 = (self.n + 15) // 16 * 16
+        self.k0dd = torch.empty((self.n, self.ld0), dtype=torch.float64, device=dev)
+        self.k0td = torch.empty((self.t, self.ld0), dtype=torch.float64, device=dev)
+        self.q_d = torch.empty(self.n, dtype=torch.float64, device=dev)
+        self.q_t = torch.empty(self.t, dtype=torch.float64, device=dev)
+        rc = self.lib.smnngp_grid_base_f64(_stream(dev), _p(x), _p(xt), self.n, self.t, d, _p(self.k0dd), self.ld0,
+                                           _p(self.k0td), self.ld0, _p(self.q_d), _p(self.q_t))
+        _lib.check(rc, "grid_base")
+
+    def point(self, hp):
+        """(mean [T], var [T], logdet, quad, info) for the scalars in ``hp`` (device operand, see make_hp)."""
+        nh, act, arch = self.spec.ids()
+        dev = self.y.device
+        mean = torch.empty(self.t, dtype=torch.float64, device=dev)
+        var = torch.empty(self.t, dtype=torch.float64, device=dev)
+        out = torch.empty(2, dtype=torch.float64, device=dev)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws_bytes = self.lib.smnngp_grid_workspace_bytes(self.n, self.t, nh, arch)
+        ws = _workspace(ws_bytes, dev)
+        rc = self.lib.smnngp_grid_point_f64(_stream(dev), _p(self.k0dd), self.ld0, _p(self.k0td), self.ld0, _p(self.q_d),
+                                            _p(self.q_t), _p(self.y), self.n, self.t, nh, act, arch, _p(hp), _p(ws),
+                                            ws_bytes, _p(mean), _p(var), _p(out), _p(info))
+        _lib.check(rc, "grid_point")
+        return mean, var, 2.0 * out[0], out[1], info
+
+
 def set_panel_width(nb: int):
     _lib.load().smnngp_set_panel_width(int(nb))
 

@@ -374,3 +374,27 @@ def test_find_grid_point(sm):
     assert np.abs(var.cpu().numpy() - var_ref).max() <= LML_TOL * np.abs(var_ref).max()
     assert abs(logdet.item() - logdet_ref) <= LML_TOL * abs(logdet_ref)
     assert abs(quad.item() - quad_ref) <= LML_TOL * abs(quad_ref)
+
+
+@pytest.mark.parametrize("n,t,d,act,arch,L", [(404, 52, 13, "relu", "mlp", 3), (900, 130, 8, "erf", "mlp", 2),
+                                              (1500, 257, 16, "relu", "resnet", 2)])
+def test_grid_search_with_cached_base(sm, n, t, d, act, arch, L):
+    """find.py grid with the base Gram cached: every point must equal the from-scratch evaluation."""
+    import torch
+    x, y, xt, yt, *_ = regression_data(n, d, t=t)
+    xd, yd, xtd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(xt).cuda()
+    spec = sm.StackSpec(L, act, arch)
+    gs = sm.device.GridSearch(xd, yd, xtd, spec=spec)
+    for w_std, b_std, eps in ((1.0, 0.3, 1e-3), (1.7, 0.05, 1e-2), (0.6, 0.9, 1e-4)):
+        hp, hpd = _hp(sm, w_std=w_std, b_std=b_std, eps=eps)
+        mean, var, logdet, quad, info = gs.point(hpd)
+        mean_ref, var_ref, logdet_ref, quad_ref = orc.find_grid_point(x, y, xt, eps, kernel_kwargs=_kw(hp, L, act, arch))
+        assert int(info.item()) == 0
+        assert np.abs(mean.cpu().numpy() - mean_ref).max() <= LML_TOL * np.abs(mean_ref).max()
+        ktt = orc.nngp_diag(xt, **_kw(hp, L, act, arch))
+        assert np.all(np.abs(var.cpu().numpy() - var_ref) <= LML_TOL * np.abs(var_ref) + 1e-13 * ktt)
+        assert abs(logdet.item() - logdet_ref) <= LML_TOL * abs(logdet_ref)
+        assert abs(quad.item() - quad_ref) <= LML_TOL * abs(quad_ref)
+        m2, v2, ld2, q2, _ = sm.device.grid_point(xd, yd, xtd, spec=spec, hp=hpd)      # from scratch
+        assert np.abs((mean - m2).cpu().numpy()).max() <= 1e-11 * np.abs(mean_ref).max()
+        assert abs(logdet.item() - ld2.item()) <= 1e-11 * abs(logdet_ref)
