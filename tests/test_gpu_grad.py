@@ -145,3 +145,31 @@ def test_spr_loss_and_grad_chain_rule(sm):
     scale = max(abs(v) for v in want.values())
     for k in want:
         assert abs(grads[k] - want[k]) <= GRAD_TOL * abs(want[k]) + 1e-12 * scale, (k, grads[k], want[k])
+
+
+def test_grad_matches_finite_differences_of_the_device_value_at_scale(sm):
+    """Size-independent property for sizes the CPU oracle cannot reach (its dual Gram needs ~15 N^2 doubles): the
+    analytic gradient must agree with central differences of the DEVICE value (smnngp_lml_f64) in every one of the
+    six scalars.  N = 9000 runs the 512-wide outer panels with look-ahead, i.e. the C3 code path."""
+    import torch
+    n, d = 9000, 64
+    x, y, *_ = regression_data(n, d)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    spec = sm.StackSpec(3, "relu", "mlp")
+    hp = dict(w_std=1.3, b_std=0.4, last_w_std=0.8, eps=1e-2, alpha=2.5, beta=1.5)
+
+    def value(h):
+        out, info = sm.device.lml(xd, yd, spec=spec, hp=torch.from_numpy(_hp_vec(h)).cuda(), kind="student_t")
+        assert int(info.item()) == 0
+        return float(out[1].item())
+
+    out, grad, info = _run(sm, x, y, hp, 3, "relu", "mlp", "student_t")
+    assert info == 0 and out[1] == value(hp)
+    for i, name in enumerate(NAMES):
+        h = 1e-4 * hp[name]
+        up, dn = dict(hp), dict(hp)
+        up[name] += h
+        dn[name] -= h
+        fd = (value(up) - value(dn)) / (2 * h)
+        # truncation ~h^2 f''' and round-off ~1e-15 |loss| / h: 1e-5 relative + an absolute floor
+        assert abs(grad[i] - fd) <= 2e-5 * abs(fd) + 1e-9, f"{name}: analytic {grad[i]} vs central difference {fd}"
