@@ -177,6 +177,11 @@ int smnngp_stage_update_f64(void* stream, const double* A, int64_t lda, const do
                             int64_t ldc, int64_t M, int64_t N, int64_t K, int lower, int64_t cyc_db, int64_t cyc_p,
                             int64_t base_shift, int sm_reserve);
 int smnngp_stage_sumsq_f64(void* stream, const double* z, int64_t n, double* out_dev);
+/* predictive tail on rows carried through the (distributed) factorisation: V [T, ldv] = K_td L^-T, Z [C, ldz] =
+ * (L^-1 Y)^T, ktt [T] -> mean [T, C] = V Z^T, var [T] = ktt - ||v||^2 (spax/kernels.py:29-32; NaN when *info_dev != 0) */
+int smnngp_stage_predict_finalize_f64(void* stream, const double* V, int64_t ldv, const double* Z, int64_t ldz,
+                                      const double* ktt, int64_t T, int64_t C, int64_t N, const int* info_dev,
+                                      double* mean, double* var);
 int smnngp_stage_lml_finalize_f64(void* stream, const double* sums_dev, const double* hp_dev, int kind, int64_t N,
                                   const int* info_dev, double* out_dev);
 

@@ -103,6 +103,18 @@ int smnngp_stage_update_f64(void* stream, const double* A, int64_t lda, const do
   return fail_stage(e);
 }
 
+// predictive tail for carried rows: V [T, ldv] = K_td L^-T rows, Z [C, ldz] = (L^-1 Y)^T rows, ktt [T] prior variances
+// -> mean [T, C] = V Z^T, var [T] = ktt - ||v||^2   (NaN when *info_dev != 0)
+int smnngp_stage_predict_finalize_f64(void* stream, const double* V, int64_t ldv, const double* Z, int64_t ldz,
+                                      const double* ktt, int64_t T, int64_t C, int64_t N, const int* info_dev,
+                                      double* mean, double* var) {
+  if (!V || !Z || !ktt || !info_dev || !mean || !var || T < 0 || C <= 0 || N <= 0 || T > INT32_MAX || C > INT32_MAX)
+    return SMNNGP_EINVAL;
+  if (T == 0) return SMNNGP_OK;
+  return fail_stage(launch_predict_finalize(static_cast<cudaStream_t>(stream), V, ldv, Z, ldz, ktt, (int)T, (int)C, N,
+                                            info_dev, mean, var));
+}
+
 int smnngp_stage_sumsq_f64(void* stream, const double* z, int64_t n, double* out_dev) {
   if (!z || !out_dev || n < 0) return SMNNGP_EINVAL;
   return fail_stage(launch_sumsq(static_cast<cudaStream_t>(stream), z, n, out_dev));

@@ -133,6 +133,17 @@ class CudaBackend:
     def sumsq(self, z, out):
         self._ck(self.lib.smnngp_stage_sumsq_f64(self._s(), self._p(z), z.shape[0], self._p(out)), "sumsq")
 
+    def predict_finalize(self, v, z, ktt, info):
+        """V [T, n] = K_td L^-T rows, Z [C, n] = (L^-1 Y)^T rows -> (mean [T, C], var [T])"""
+        t, n = v.shape
+        c = z.shape[0]
+        mean, var = self.empty(t, c), self.empty(t)
+        if t > 0:
+            self._ck(self.lib.smnngp_stage_predict_finalize_f64(self._s(), self._p(v), v.stride(0), self._p(z),
+                                                                z.stride(0), self._p(ktt), t, c, n, self._p(info),
+                                                                self._p(mean), self._p(var)), "predict_finalize")
+        return mean, var
+
     def lml_finalize(self, sums, hp, kind, n, info):
         out = self.empty(4)
         self._ck(self.lib.smnngp_stage_lml_finalize_f64(self._s(), self._p(sums), self._p(hp), KIND[kind], n,
@@ -241,7 +252,7 @@ class DistributedLML:
     is fixed, every rank owns ~1/P of the rows."""
 
     def __init__(self, n, d, spec: StackSpec, device, group=None, block=None, backend=None, emulate=None,
-                 exchange="auto"):
+                 exchange="auto", extra_rows=1):
         """emulate=(world, rank): timing dry-run of ONE rank's work of a `world`-rank job on a single device - the
         collectives are replaced by local copies of the same size, so the numbers it produces are meaningless but
         every kernel launch has the shape it has in the real job (used to profile the schedule at 1 GPU cost)."""
@@ -258,7 +269,11 @@ class DistributedLML:
         self._gidx = {}
         self.db = int(block) if block else default_block(self.n, self.world)
         self.be = backend if backend is not None else CudaBackend(device)
-        self.lay = BlockRowCyclic(self.n + 1, self.n, self.world, self.rank, self.db)
+        # rows below the square part are carried through the factorisation (rows * L^-T): y^T here, the right-hand
+        # sides and the test-train cross-Gram in DistributedPredict
+        self.n_extra = int(extra_rows)
+        self.gram_shift = "eps_abs"                                      # K + eps I (spax/models.py:96)
+        self.lay = BlockRowCyclic(self.n + self.n_extra, self.n, self.world, self.rank, self.db)
         self.ld = _cdiv(self.n, 16) * 16
         self.mloc = self.lay.local_rows()
         self.a = self.be.empty(max(self.mloc, 1), self.ld)
@@ -326,10 +341,16 @@ class DistributedLML:
                 if g0 > 0:                                               # rectangle left of the diagonal block
                     be.gram_block(xb, x[:g0], self.spec, hp, tab[:, g0:], tab, scal, "none", False,
                                   self.a[lo:lo + rows, :g0])
-                be.gram_block(xb, xb, self.spec, hp, tab[:, g0:], tab[:, g0:], scal, "eps_abs", True,
-                              self.a[lo:lo + rows, g0:g0 + rows])       # K + eps I (spax/models.py:96)
-            if g0 <= n < g0 + lay.block_rows(b):                         # the appended row y^T
-                self.a[lo + (n - g0), :n].copy_(y)
+                be.gram_block(xb, xb, self.spec, hp, tab[:, g0:], tab[:, g0:], scal, self.gram_shift, True,
+                              self.a[lo:lo + rows, g0:g0 + rows])
+            if g0 + lay.block_rows(b) > n:                               # this block holds carried rows
+                self._fill_extra_rows(b, g0, lo, x, y, hp, tab, scal)
+
+    def _fill_extra_rows(self, b, g0, lo, x, y, hp, tab, scal):
+        """the appended row y^T (global row n)"""
+        n = self.n
+        if g0 <= n < g0 + self.lay.block_rows(b):
+            self.a[lo + (n - g0), :n].copy_(y)
 
     def _gather_index(self, p, c1):
         """position of global rows [c1, N) inside the padded all-gather buffer (rank-major)"""
@@ -482,9 +503,29 @@ class DistributedLML:
         return ls, m, pfull
 
     def lml(self, x, y, hp, kind="student_t"):
-        """Right-looking factorisation with one panel of look-ahead: while the bulk of panel p's trailing update
-        runs on the main stream, the next panel (diagonal block, broadcast, TRSM, all-gather) is prepared on a
-        side stream as soon as its block column has been updated."""
+        """SPR.loss pieces: (out[4] = {log p, loss, sum log L_ii, ||L^-1 y||^2}, info), identical on every rank."""
+        be, lay, n, db, P = self.be, self.lay, self.n, self.db, self.world
+        sums, info, npanels = self._factor(x, y, hp)
+        # z = (L^-1 y)^T sits in global row N on its owner
+        bn = n // db
+        if self.rank == lay.owner(bn):
+            if self.px is not None:
+                be.sumsq(self.zvec, sums[1:2])
+            else:
+                lrow = lay.local_offset(bn) + (n - bn * db)
+                be.sumsq(self.a[lrow, :n], sums[1:2])
+        if self.px is not None:
+            self.seq_base += npanels + 1
+        if P > 1 and not self.emulate:
+            dist.all_reduce(sums, group=self.group)
+            dist.all_reduce(info, op=dist.ReduceOp.MAX, group=self.group)
+        return be.lml_finalize(sums, hp, kind, n, info), info
+
+    def _factor(self, x, y, hp):
+        """Gram build + right-looking factorisation with one panel of look-ahead: while the bulk of panel p's trailing
+        update runs on the main stream, the next panel (diagonal block, broadcast, TRSM, all-gather) is prepared on a
+        side stream as soon as its block column has been updated.  Returns (sums, info, npanels); sums[0] = this rank's
+        part of sum log L_ii."""
         be, lay, n, db, P = self.be, self.lay, self.n, self.db, self.world
         self._build_gram(x, y, hp)
         sums = be.zeros(2)
@@ -545,20 +586,79 @@ class DistributedLML:
             cur = nxt
         if cuda:
             main.wait_stream(side)
-        # z = (L^-1 y)^T sits in global row N on its owner
-        bn = n // db
-        if self.rank == lay.owner(bn):
-            if self.px is not None:
-                be.sumsq(self.zvec, sums[1:2])
-            else:
-                lrow = lay.local_offset(bn) + (n - bn * db)
-                be.sumsq(self.a[lrow, :n], sums[1:2])
+        return sums, info, npanels
+
+
+class DistributedPredict(DistributedLML):
+    """NNGPKernel.predict (spax/kernels.py:29-32: neural_tangents gradient_descent_mse_ensemble, relative regulariser
+    eps tr(K)/N) on the ranks of a process group.  The C right-hand sides Y^T and the T rows of the test-train
+    cross-Gram are carried through the distributed factorisation as extra global rows n .. n+C+T-1 of the same
+    block-row-cyclic layout (they are never exchanged: only square rows enter the panel all-gather), so every rank
+    ends up with (L^-1 K_dt)^T for ITS test points; the C rows (L^-1 Y)^T are summed to every rank and the predictive
+    tail is the single-GPU kernel on local rows."""
+
+    def __init__(self, n, d, t, c, spec: StackSpec, device, **kw):
+        super().__init__(n, d, spec, device, extra_rows=int(c) + int(t), **kw)
+        self.t, self.c = int(t), int(c)
+        self.gram_shift = "eps_rel"
+        lay = self.lay
+        g = [torch.arange(b * self.db, b * self.db + lay.block_rows(b)) for b in lay.local_blocks()]
+        g = torch.cat(g) if g else torch.zeros(0, dtype=torch.int64)
+        self.extra_lo = int((g < self.n).sum())                  # local storage keeps global order: carried rows = tail
+        self.extra_idx = (g[self.extra_lo:] - self.n).to(self.a.device)     # position inside [Y^T rows | test rows]
+        if self.px is not None:
+            self.carried = self.be.zeros(max(int(self.extra_idx.numel()), 1), self.n)
+
+    def _fill_extra_rows(self, b, g0, lo, x, y, hp, tab, scal):
+        n, c = self.n, self.c
+        g1 = g0 + self.lay.block_rows(b)
+        for j in range(max(g0, n), min(g1, n + c)):             # right-hand sides: global rows n .. n+c-1
+            self.a[lo + (j - g0), :n].copy_(self._Y[:, j - n])
+        t0, t1 = max(g0, n + c) - (n + c), g1 - (n + c)         # test points held by this block
+        if t1 > t0:
+            r0 = lo + (n + c + t0 - g0)
+            self.be.gram_block(self._xt[t0:t1], x, self.spec, hp, self._tab_t[:, t0:], tab, scal, "none", False,
+                               self.a[r0:r0 + (t1 - t0), :n])
+
+    def _panel(self, p, sums, info, slot):
+        res = super()._panel(p, sums, info, slot)
+        if self.px is not None:                                   # peer exchange: solved rows live in ploc only
+            ls, m = res[0], res[1]
+            k = self.extra_lo - ls
+            if m > k:
+                c0, c1 = p * self.db, min((p + 1) * self.db, self.n)
+                self.carried[:m - k, c0:c1].copy_(self.ploc[p & 1][k:m, :c1 - c0])
+        return res
+
+    def predict(self, x, y, x_test, hp):
+        """(mean [T, C], var [T] = diag of the posterior covariance, info) - identical on every rank."""
+        be, n, c, t, P = self.be, self.n, self.c, self.t, self.world
+        self._Y = y if y.ndim == 2 else y[:, None]
+        self._xt = x_test
+        self._tab_t, q_t, _ = be.qtable(x_test, self.spec, hp)
+        sums, info, npanels = self._factor(x, self._Y[:, 0], hp)
         if self.px is not None:
             self.seq_base += npanels + 1
-        if P > 1 and not self.emulate:
-            dist.all_reduce(sums, group=self.group)
+        rows = self.carried if self.px is not None else self.a[self.extra_lo:self.mloc, :n]
+        idx = self.extra_idx
+        z = be.zeros(c, n)
+        is_rhs = idx < c
+        if bool(is_rhs.any()):
+            z[idx[is_rhs]] = rows[:idx.numel()][is_rhs]
+        multi = P > 1 and not self.emulate
+        if multi:
+            dist.all_reduce(z, group=self.group)
             dist.all_reduce(info, op=dist.ReduceOp.MAX, group=self.group)
-        return be.lml_finalize(sums, hp, kind, n, info), info
+        ti = idx[~is_rhs] - c                                      # this rank's test points
+        v = rows[:idx.numel()][~is_rhs].contiguous()
+        mean_l, var_l = be.predict_finalize(v, z, q_t[ti].contiguous(), info)
+        mean, var = be.zeros(t, c), be.zeros(t)
+        mean[ti] = mean_l
+        var[ti] = var_l
+        if multi:
+            dist.all_reduce(mean, group=self.group)
+            dist.all_reduce(var, group=self.group)
+        return mean, var, info
 
 
 class _NullCtx:

@@ -19,7 +19,12 @@ class NumpyBackend:
 
     def qtable(self, x, spec, hp):
         n = x.shape[0]
-        return torch.zeros(1, n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64), torch.zeros(16, dtype=torch.float64)
+        w, b, v = (float(hp[i]) for i in range(3))
+        q = torch.from_numpy(orc.nngp_diag(x.numpy(), num_hiddens=spec.num_hiddens, act=spec.act, arch=spec.arch,
+                                           w_std=w, b_std=b, last_w_std=v))
+        scal = torch.zeros(16, dtype=torch.float64)
+        scal[0] = q.mean()                                    # tr(K) / N, as the device scalar block carries it
+        return torch.zeros(1, n, dtype=torch.float64), q, scal
 
     def gram_block(self, x1, x2, spec, hp, tab1, tab2, scal, shift, symmetric_lower, out):
         w, b, v, eps = (float(hp[i]) for i in range(4))
@@ -29,6 +34,8 @@ class NumpyBackend:
         if symmetric_lower:
             if shift == "eps_abs":
                 k = k + eps * np.eye(k.shape[0])
+            elif shift == "eps_rel":                              # neural_tangents diag_reg: eps tr(K) / N
+                k = k + eps * float(scal[0]) * np.eye(k.shape[0])
             il = np.tril_indices(k.shape[0])
             o[il] = k[il]
         else:
@@ -65,6 +72,14 @@ class NumpyBackend:
 
     def sumsq(self, z, out):
         out[0] = float((z.numpy() ** 2).sum())
+
+    def predict_finalize(self, v, z, ktt, info):
+        vn, zn = v.numpy(), z.numpy()
+        mean = torch.from_numpy(vn @ zn.T)
+        var = torch.from_numpy(ktt.numpy() - (vn * vn).sum(axis=1))
+        if int(info[0]) != 0:
+            mean, var = mean * float("nan"), var * float("nan")
+        return mean, var
 
     def lml_finalize(self, sums, hp, kind, n, info):
         from scipy.special import gammaln

@@ -56,6 +56,60 @@ def test_block_row_cyclic_lml_matches_oracle(world, n, db, kind):
     assert res[0][1] == res[1][1], "every rank must hold the same result"
 
 
+def _predict_worker(rank, world, port, n, t, c, d, db, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import smnngp_b200 as sm
+        from smnngp_b200.distributed import DistributedPredict
+        from tests.np_backend import NumpyBackend
+        from tests.synth import regression_data, DEFAULT_HP as hp
+        x, y, xt, *_ = regression_data(n, d, t=t)
+        rng = np.random.default_rng(5)
+        Y = np.column_stack([y] + [rng.standard_normal(n) for _ in range(c - 1)])
+        spec = sm.StackSpec(3, "relu", "mlp")
+        hpt = torch.tensor([hp[k] for k in ("w_std", "b_std", "last_w_std", "eps", "alpha", "beta")], dtype=torch.float64)
+        solver = DistributedPredict(n, d, t, c, spec, "cpu", block=db, backend=NumpyBackend())
+        mean, var, info = solver.predict(torch.from_numpy(x), torch.from_numpy(Y), torch.from_numpy(xt), hpt)
+        q.put((rank, mean.numpy(), var.numpy(), int(info[0])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,t,c,db", [(2, 700, 130, 2, 128), (3, 600, 300, 1, 128), (2, 512, 40, 3, 256),
+                                            (2, 300, 5, 1, 128)])
+def test_block_row_cyclic_predict_matches_oracle(world, n, t, c, db):
+    """right-hand sides and test-train rows carried through the distributed factorisation (NCCL-style exchange,
+    NumPy arithmetic): NNGPKernel.predict with the relative regulariser"""
+    from oracle import nngp_oracle as orc
+    from tests.synth import regression_data, DEFAULT_HP as hp
+    d = 6
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + n + t) % 2000
+    procs = [ctx.Process(target=_predict_worker, args=(r, world, port, n, t, c, d, db, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, y, xt, *_ = regression_data(n, d, t=t)
+    rng = np.random.default_rng(5)
+    Y = np.column_stack([y] + [rng.standard_normal(n) for _ in range(c - 1)])
+    kw = dict(num_hiddens=3, act="relu", arch="mlp", w_std=hp["w_std"], b_std=hp["b_std"], last_w_std=hp["last_w_std"])
+    mean_ref, cov_ref = orc.nt_predict(x, Y, xt, hp["eps"], kernel_kwargs=kw)
+    vref = np.diag(cov_ref)
+    ktt = orc.nngp_diag(xt, **kw)
+    for rank, mean, var, info in res:
+        assert info == 0 and mean.shape == (t, c) and var.shape == (t,)
+        assert np.abs(mean - mean_ref).max() <= 1e-8 * np.abs(mean_ref).max(), rank
+        assert np.all(np.abs(var - vref) <= 1e-8 * np.abs(vref) + 1e-12 * ktt), rank
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+
+
 def test_layout_bookkeeping():
     from smnngp_b200.distributed import BlockRowCyclic
     for (m, P, db) in [(701, 2, 128), (1025, 3, 256), (60001, 8, 512), (513, 4, 128), (129, 2, 128)]:

@@ -102,3 +102,61 @@ def test_emulated_rank_schedule_runs_on_one_gpu():
     labels = {lab for _, lab, _ in job.timeline}
     assert {"main_start", "update_a", "update_b", "diag", "trsm", "gather"} <= labels
     job.px.close()
+
+
+def _predict_worker(rank, world, port, n, t, c, d, db, q, exchange):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import smnngp_b200 as sm
+        from smnngp_b200.distributed import DistributedPredict
+        from tests.synth import regression_data, DEFAULT_HP as hp
+        x, y, xt, *_ = regression_data(n, d, t=t)
+        rng = np.random.default_rng(5)
+        Y = np.column_stack([y] + [rng.standard_normal(n) for _ in range(c - 1)])
+        dev = torch.device("cuda", rank)
+        solver = DistributedPredict(n, d, t, c, sm.StackSpec(3, "relu", "mlp"), dev, block=db, exchange=exchange)
+        mean, var, info = solver.predict(torch.from_numpy(x).to(dev), torch.from_numpy(Y).to(dev),
+                                         torch.from_numpy(xt).to(dev), sm.make_hp(device=dev, **hp))
+        q.put((rank, mean.cpu().numpy(), var.cpu().numpy(), int(info.item())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(os.environ.get("SMNNGP_TEST_DIST_PREDICT") != "1",
+                    reason="DistributedPredict is validated under gloo on CPU (tests/test_distributed_cpu.py); its first "
+                           "2-GPU run is pending (round 1 ran out of GPU budget) - opt in with SMNNGP_TEST_DIST_PREDICT=1")
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("n,t,c,db", [(1500, 300, 2, 128), (3000, 700, 1, 256)])
+def test_two_rank_predict_matches_oracle(n, t, c, db, exchange):
+    import torch
+    import torch.multiprocessing as mp
+    from oracle import nngp_oracle as orc
+    from tests.synth import regression_data, DEFAULT_HP as hp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + n % 100 + (50 if exchange == "peer" else 0)
+    procs = [ctx.Process(target=_predict_worker, args=(r, 2, port, n, t, c, 8, db, q, exchange)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, y, xt, *_ = regression_data(n, 8, t=t)
+    rng = np.random.default_rng(5)
+    Y = np.column_stack([y] + [rng.standard_normal(n) for _ in range(c - 1)])
+    kw = dict(num_hiddens=3, act="relu", arch="mlp", w_std=hp["w_std"], b_std=hp["b_std"], last_w_std=hp["last_w_std"])
+    mean_ref, cov_ref = orc.nt_predict(x, Y, xt, hp["eps"], kernel_kwargs=kw)
+    vref, ktt = np.diag(cov_ref), orc.nngp_diag(xt, **kw)
+    for rank, mean, var, info in res:
+        assert info == 0
+        assert np.abs(mean - mean_ref).max() <= 1e-8 * np.abs(mean_ref).max()
+        assert np.all(np.abs(var - vref) <= 1e-8 * np.abs(vref) + 1e-13 * ktt)
