@@ -179,6 +179,12 @@ int smnngp_stage_update_f64(void* stream, const double* A, int64_t lda, const do
 int smnngp_stage_sumsq_f64(void* stream, const double* z, int64_t n, double* out_dev);
 /* predictive tail on rows carried through the (distributed) factorisation: V [T, ldv] = K_td L^-T, Z [C, ldz] =
  * (L^-1 Y)^T, ktt [T] -> mean [T, C] = V Z^T, var [T] = ktt - ||v||^2 (spax/kernels.py:29-32; NaN when *info_dev != 0) */
+/* SPR.test_nll tail (spax/models.py:114-119 with Likelihood.logpdf, spax/likelihoods.py:30-33 / :52-65) on predictive
+ * moments: de-standardisation, per-point log density (logp [T], may be NULL) and nll_out_dev[1] = -mean.  quad2_dev =
+ * ||L2^-1 y||^2 of the factorisation of K + 1e-6 (alpha/beta) I (Student-t; NULL allowed for gauss) */
+int smnngp_stage_test_nll_finalize_f64(void* stream, const double* mean, const double* var, const double* ytest,
+                                       int64_t T, int64_t N, double y_mean, double y_std, const double* hp_dev, int kind,
+                                       const double* quad2_dev, const int* info_dev, double* logp, double* nll_out_dev);
 int smnngp_stage_predict_finalize_f64(void* stream, const double* V, int64_t ldv, const double* Z, int64_t ldz,
                                       const double* ktt, int64_t T, int64_t C, int64_t N, const int* info_dev,
                                       double* mean, double* var);

@@ -30,7 +30,7 @@ EXPORTS = [
     "smnngp_grid_base_f64", "smnngp_grid_workspace_bytes", "smnngp_grid_point_f64",
     "smnngp_stage_qtable_f64", "smnngp_stage_gram_f64", "smnngp_stage_factor_diag_f64", "smnngp_stage_trsm_f64",
     "smnngp_stage_update_f64", "smnngp_stage_sumsq_f64", "smnngp_stage_lml_finalize_f64",
-    "smnngp_stage_predict_finalize_f64",
+    "smnngp_stage_predict_finalize_f64", "smnngp_stage_test_nll_finalize_f64",
     "smnngp_stage_factor_diag_inv_f64", "smnngp_stage_scatter_inverse_f64", "smnngp_stage_signal_f64",
     "smnngp_stage_wait_flags_f64", "smnngp_stage_trsm_scatter_f64", "smnngp_set_peer_wait_mode",
     "smnngp_stage_push_panel_f64",
@@ -149,6 +149,8 @@ def _declare(lib):
     lib.smnngp_stage_update_f64.argtypes = [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i, _i64, _i64,
                                             _i64, _i]
     lib.smnngp_stage_sumsq_f64.argtypes = [_vp, _vp, _i64, _vp]
+    lib.smnngp_stage_test_nll_finalize_f64.argtypes = [_vp, _vp, _vp, _vp, _i64, _i64, _d, _d, _vp, _i, _vp, _vp, _vp,
+                                                       _vp]
     lib.smnngp_stage_predict_finalize_f64.argtypes = [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp]
     lib.smnngp_stage_lml_finalize_f64.argtypes = [_vp, _vp, _vp, _i, _i64, _vp, _vp]
     _u64, _u = C.c_uint64, C.c_int

@@ -115,6 +115,19 @@ int smnngp_stage_predict_finalize_f64(void* stream, const double* V, int64_t ldv
                                             info_dev, mean, var));
 }
 
+// SPR.test_nll tail (spax/models.py:114-119, spax/likelihoods.py:30-33 / :52-65) on gathered predictive moments:
+// quad2_dev = ||L2^-1 y||^2 of the second factorisation K + 1e-6 (alpha/beta) I (Student-t only; may be NULL for gauss)
+int smnngp_stage_test_nll_finalize_f64(void* stream, const double* mean, const double* var, const double* ytest,
+                                       int64_t T, int64_t N, double y_mean, double y_std, const double* hp_dev, int kind,
+                                       const double* quad2_dev, const int* info_dev, double* logp, double* nll_out_dev) {
+  if (!mean || !var || !ytest || !hp_dev || !info_dev || !nll_out_dev || T <= 0 || T > INT32_MAX ||
+      (kind != KIND_GAUSS && kind != KIND_STUDENT_T) || (kind == KIND_STUDENT_T && !quad2_dev))
+    return SMNNGP_EINVAL;
+  return fail_stage(launch_test_nll_finalize(static_cast<cudaStream_t>(stream), mean, var, ytest, (int)T, N, y_mean,
+                                             y_std, hp_dev, kind, quad2_dev ? quad2_dev : mean, info_dev, logp,
+                                             nll_out_dev));
+}
+
 int smnngp_stage_sumsq_f64(void* stream, const double* z, int64_t n, double* out_dev) {
   if (!z || !out_dev || n < 0) return SMNNGP_EINVAL;
   return fail_stage(launch_sumsq(static_cast<cudaStream_t>(stream), z, n, out_dev));

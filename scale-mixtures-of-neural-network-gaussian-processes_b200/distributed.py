@@ -144,6 +144,15 @@ class CudaBackend:
                                                                 self._p(mean), self._p(var)), "predict_finalize")
         return mean, var
 
+    def test_nll_finalize(self, mean, var, ytest, n, y_mean, y_std, hp, kind, quad2, info):
+        out = self.empty(1)
+        q2 = self._p(quad2) if quad2 is not None else C.c_void_p(0)
+        self._ck(self.lib.smnngp_stage_test_nll_finalize_f64(self._s(), self._p(mean), self._p(var), self._p(ytest),
+                                                             mean.shape[0], n, float(y_mean), float(y_std),
+                                                             self._p(hp), KIND[kind], q2, self._p(info), C.c_void_p(0),
+                                                             self._p(out)), "test_nll_finalize")
+        return out
+
     def lml_finalize(self, sums, hp, kind, n, info):
         out = self.empty(4)
         self._ck(self.lib.smnngp_stage_lml_finalize_f64(self._s(), self._p(sums), self._p(hp), KIND[kind], n,
@@ -608,6 +617,7 @@ class DistributedPredict(DistributedLML):
         self.extra_idx = (g[self.extra_lo:] - self.n).to(self.a.device)     # position inside [Y^T rows | test rows]
         if self.px is not None:
             self.carried = self.be.zeros(max(int(self.extra_idx.numel()), 1), self.n)
+        self._lik = None
 
     def _fill_extra_rows(self, b, g0, lo, x, y, hp, tab, scal):
         n, c = self.n, self.c
@@ -659,6 +669,28 @@ class DistributedPredict(DistributedLML):
             dist.all_reduce(mean, group=self.group)
             dist.all_reduce(var, group=self.group)
         return mean, var, info
+
+    def test_nll(self, x, y, x_test, y_test, y_mean, y_std, hp, kind="student_t"):
+        """SPR.test_nll (spax/models.py:100-120): the predictive above (relative regulariser, one right-hand side) +,
+        for the Student-t likelihood, the scale d = 2a + y^T ((b/a) K + 1e-6 I)^-1 y (spax/likelihoods.py:60-61) from a
+        SECOND distributed factorisation of K + 1e-6 (a/b) I, then the closed-form tail.  Returns (nll [1], mean [T],
+        var [T], info), identical on every rank."""
+        if self.c != 1:
+            raise ValueError("test_nll needs a DistributedPredict built with c = 1")
+        mean, var, info = self.predict(x, y, x_test, hp)
+        quad2 = None
+        if kind == "student_t":
+            if self._lik is None:                                 # plain LML driver with the likelihood's jitter
+                self._lik = DistributedLML(self.n, self.d, self.spec, self.a.device, group=self.group, block=self.db,
+                                           backend=self.be, exchange=self.exchange,
+                                           emulate=(self.world, self.rank) if self.emulate else None)
+                self._lik.gram_shift = "lik"
+            out2, info2 = self._lik.lml(x, y if y.ndim == 1 else y[:, 0], hp, kind="gauss")
+            quad2 = out2[3:4].contiguous()                        # ||L2^-1 y||^2
+            info = torch.maximum(info, info2)
+        nll = self.be.test_nll_finalize(mean[:, 0].contiguous(), var, y_test, self.n, y_mean, y_std, hp, kind, quad2,
+                                        info)
+        return nll, mean[:, 0], var, info
 
 
 class _NullCtx:

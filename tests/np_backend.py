@@ -36,6 +36,8 @@ class NumpyBackend:
                 k = k + eps * np.eye(k.shape[0])
             elif shift == "eps_rel":                              # neural_tangents diag_reg: eps tr(K) / N
                 k = k + eps * float(scal[0]) * np.eye(k.shape[0])
+            elif shift == "lik":                                  # (b/a) K + 1e-6 I = (b/a) (K + 1e-6 (a/b) I)
+                k = k + 1e-6 * float(hp[4]) / float(hp[5]) * np.eye(k.shape[0])
             il = np.tril_indices(k.shape[0])
             o[il] = k[il]
         else:
@@ -80,6 +82,22 @@ class NumpyBackend:
         if int(info[0]) != 0:
             mean, var = mean * float("nan"), var * float("nan")
         return mean, var
+
+    def test_nll_finalize(self, mean, var, ytest, n, y_mean, y_std, hp, kind, quad2, info):
+        a, b = float(hp[4]), float(hp[5])
+        xx = ytest.numpy() * y_std + y_mean
+        mm = mean.numpy() * y_std + y_mean
+        cv = var.numpy() * y_std ** 2
+        if kind == "student_t":
+            df = 2 * a
+            cond_df = df + n
+            d = df + (a / b) * float(quad2[0])
+            lp = orc._t_logpdf(xx, cond_df, mm, np.sqrt(d / cond_df * b / a * cv))
+        else:
+            sg = np.sqrt(cv)
+            lp = -0.5 * np.log(2 * np.pi) - np.log(sg) - 0.5 * ((xx - mm) / sg) ** 2
+        nll = -float(np.mean(lp)) if int(info[0]) == 0 else float("nan")
+        return torch.tensor([nll], dtype=torch.float64)
 
     def lml_finalize(self, sums, hp, kind, n, info):
         from scipy.special import gammaln

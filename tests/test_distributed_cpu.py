@@ -110,6 +110,50 @@ def test_block_row_cyclic_predict_matches_oracle(world, n, t, c, db):
     assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
 
 
+def _nll_worker(rank, world, port, n, t, d, db, kind, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import smnngp_b200 as sm
+        from smnngp_b200.distributed import DistributedPredict
+        from tests.np_backend import NumpyBackend
+        from tests.synth import regression_data, DEFAULT_HP as hp
+        x, y, xt, yt, ym, ys = regression_data(n, d, t=t)
+        hpt = torch.tensor([hp[k] for k in ("w_std", "b_std", "last_w_std", "eps", "alpha", "beta")], dtype=torch.float64)
+        solver = DistributedPredict(n, d, t, 1, sm.StackSpec(3, "relu", "mlp"), "cpu", block=db, backend=NumpyBackend())
+        nll, mean, var, info = solver.test_nll(torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(xt),
+                                               torch.from_numpy(yt), ym, ys, hpt, kind=kind)
+        q.put((rank, float(nll[0]), int(info[0])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,t,db,kind", [(2, 600, 70, 128, "student_t"), (3, 500, 60, 128, "gauss")])
+def test_block_row_cyclic_test_nll_matches_oracle(world, n, t, db, kind):
+    """SPR.test_nll on P ranks: predictive + second factorisation with the likelihood's jitter + closed-form tail"""
+    from oracle import nngp_oracle as orc
+    from tests.synth import regression_data, DEFAULT_HP as hp
+    d = 6
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() + n + t) % 2000
+    procs = [ctx.Process(target=_nll_worker, args=(r, world, port, n, t, d, db, kind, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, y, xt, yt, ym, ys = regression_data(n, d, t=t)
+    ref = orc.spr_test_nll(x, y, xt, yt, ym, ys, num_hiddens=3, act="relu", arch="mlp", w_std=hp["w_std"],
+                           b_std=hp["b_std"], last_w_std=hp["last_w_std"], eps=hp["eps"], kind=kind, a=hp["alpha"],
+                           b=hp["beta"])
+    for rank, nll, info in res:
+        assert info == 0 and abs(nll - ref) <= 1e-8 * abs(ref), (rank, nll, ref)
+
+
 def test_layout_bookkeeping():
     from smnngp_b200.distributed import BlockRowCyclic
     for (m, P, db) in [(701, 2, 128), (1025, 3, 256), (60001, 8, 512), (513, 4, 128), (129, 2, 128)]:
