@@ -238,6 +238,8 @@ class PeerExchange:
         return (C.c_void_p * self.world)(*[b + off for b in self.bases])
 
     def close(self):
+        self.w_local = None                     # views of the region: must not outlive it
+        self.panel_local = []
         for p in self._opened:
             self.lib.smnngp_peer_close(C.c_void_p(p))
         self._opened = []
