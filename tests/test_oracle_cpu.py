@@ -67,6 +67,45 @@ def test_oracle_gram_dual_matches_finite_differences():
             assert np.abs(fd - d).max() <= 1e-8 * max(np.abs(d).max(), 1.0), name
 
 
+def test_oracle_dual_homogeneity_identities():
+    """Analytic identities of the recursion's derivatives: with b_std = 0 the ReLU NNGP kernel is homogeneous of
+    degree 2L in w_std (w dK/dw = 2L K, mlp) and every stack is homogeneous of degree 2 in last_w_std."""
+    rng = np.random.default_rng(11)
+    x, x2 = rng.standard_normal((30, 5)), rng.standard_normal((12, 5))
+    for L in (1, 3):
+        K, dw, db, dv = orc.nngp_gram_dual(x, x2, num_hiddens=L, act="relu", arch="mlp", w_std=1.3, b_std=0.0,
+                                           last_w_std=0.7)
+        assert np.abs(1.3 * dw - 2 * L * K).max() <= 1e-13 * np.abs(K).max()
+        assert np.abs(db).max() == 0.0                      # d/db of b^2 at b = 0
+        assert np.abs(0.7 * dv - 2 * K).max() <= 1e-14 * np.abs(K).max()
+    for act, arch in (("erf", "mlp"), ("relu", "resnet"), ("erf", "resnet")):
+        K, dw, db, dv = orc.nngp_gram_dual(x, x2, num_hiddens=2, act=act, arch=arch, w_std=0.9, b_std=0.4,
+                                           last_w_std=1.6)
+        assert np.abs(1.6 * dv - 2 * K).max() <= 1e-14 * np.abs(K).max()
+
+
+def test_oracle_loss_invariances():
+    """SPR.loss does not depend on the order of the data; for the Gaussian likelihood scaling (last_w_std, eps, y)
+    by (c, c^2, c) shifts log p by -N log c exactly."""
+    x, y, *_ = __import__("tests.synth", fromlist=["regression_data"]).regression_data(120, 7)
+    kw = dict(num_hiddens=3, act="relu", arch="mlp", w_std=1.1, b_std=0.3)
+    base = orc.spr_loss(x, y, last_w_std=0.8, eps=1e-3, kind="student_t", a=2.5, b=1.5, **kw)
+    perm = np.random.default_rng(3).permutation(120)
+    assert abs(orc.spr_loss(x[perm], y[perm], last_w_std=0.8, eps=1e-3, kind="student_t", a=2.5, b=1.5, **kw) - base) \
+        <= 1e-12 * abs(base)
+    c = 1.7
+    g0 = orc.spr_loss(x, y, last_w_std=0.8, eps=1e-3, kind="gauss", **kw)
+    g1 = orc.spr_loss(x, c * y, last_w_std=0.8 * c, eps=1e-3 * c * c, kind="gauss", **kw)
+    assert abs((g1 - g0) - np.log(c)) <= 1e-12
+    # gradient consistency with that scaling law: d/dc [loss(c)] at c = 1 = 1 = v dl/dv + 2 eps dl/deps + y.dl/dy; the
+    # y-part is -(1/N) y^T d log p / d y = quad / N for the Gaussian
+    loss, grad = orc.spr_loss_grad(x, y, last_w_std=0.8, eps=1e-3, kind="gauss", **kw)
+    n = 120
+    K = orc.nngp_gram(x, last_w_std=0.8, **kw) + 1e-3 * np.eye(n)
+    quad = float(y @ np.linalg.solve(K, y))
+    assert abs(0.8 * grad[2] + 2 * 1e-3 * grad[3] + quad / n - 1.0) <= 1e-9
+
+
 def test_c_recursion_matches_numpy():
     rng = np.random.default_rng(0)
     x, x2 = rng.standard_normal((300, 7)), rng.standard_normal((111, 7))
