@@ -5,3 +5,4 @@ from .utils import jitter, multivariate_t_logpdf, multivariate_normal_logpdf
 from .base import Module, TrainVar, ConstraintTrainVar
 from .bijectors import positive
 from .priors import Prior, GaussianPrior, InverseGammaPrior
+from .optimizer import Adam

@@ -1,0 +1,77 @@
+"""The training loop of examples/regression_train.py (the reference's experiments/regression/train.py:61-67 loop) and
+the spax Adam on CPU: the device calls (loss_and_grad / test_nll) are replaced by the oracle - test infrastructure
+only - to check the host-side pieces: variable naming, softplus chain rule, the optimiser, the NaN stop."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import nngp_oracle as orc  # noqa: E402
+
+
+def _oracle_backed(model, kw_stack):
+    """patch the two device entry points of an SPR instance with oracle evaluations (same contracts)"""
+    names = ("w_std", "b_std", "last_w_std", "eps", "alpha", "beta")
+
+    def hp():
+        ws, bs, ls = model.kernel.get_params()
+        d = dict(w_std=ws, b_std=bs, last_w_std=ls, eps=model.eps.safe_value, a=2.0, b=2.0)
+        if hasattr(model.likelihood, "a"):
+            d.update(a=model.likelihood.a.safe_value, b=model.likelihood.b.safe_value)
+        return d
+
+    def loss_and_grad():
+        loss, g = orc.spr_loss_grad(model.x_data, model.y_data, kind=model.likelihood.kind, **kw_stack, **hp())
+        slots = {"kernel.w_std": (model.kernel.w_std, 0), "kernel.b_std": (model.kernel.b_std, 1),
+                 "kernel.last_w_std": (model.kernel.last_w_std, 2), "eps": (model.eps, 3)}
+        if hasattr(model.likelihood, "a"):
+            slots.update({"likelihood.a": (model.likelihood.a, 4), "likelihood.b": (model.likelihood.b, 5)})
+        return loss, {k: float(g[i]) * float(v.constraint.grad(v.value)) for k, (v, i) in slots.items()}
+
+    def test_nll(x, y):
+        return orc.spr_test_nll(model.x_data, model.y_data, x, y, model.y_mean, model.y_std, kind=model.likelihood.kind,
+                                **kw_stack, **hp())
+
+    model.loss_and_grad, model.test_nll = loss_and_grad, test_nll
+    return names
+
+
+def test_training_loop_decreases_the_loss_and_names_match():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("regression_train", os.path.join(ROOT, "examples", "regression_train.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    args = ex.parse(["--method", "tp", "--rows", "120", "--features", "5", "--max-steps", "30", "--print-interval", "10",
+                     "--valid-interval", "10", "--epsilon", "1e-3", "--b-std", "0.2", "-lr", "0.05"])
+    (x, y), valid, test, (y_std, y_mean) = ex.make_data(args.rows, 15, 15, args.features, args.seed)
+    model = ex.build_model(args, x, y, y_mean, y_std)
+    assert set(model.vars()) == {"kernel.w_std", "kernel.b_std", "kernel.last_w_std", "eps", "likelihood.a",
+                                 "likelihood.b"}
+    _oracle_backed(model, dict(num_hiddens=3, act="relu", arch="mlp"))
+    l0, g0 = model.loss_and_grad()
+    assert set(g0) == set(model.vars())
+    lines = []
+    best = ex.train(model, args, valid, test, log=lines.append)
+    l1, _ = model.loss_and_grad()
+    assert l1 < l0 - 1e-3, (l0, l1)                    # 30 Adam steps on the six scalars reduce the training loss
+    assert best[0] % 10 == 0 and np.isfinite(best[1])
+    assert any("nll:" in s for s in lines) and any("TEST:" in s for s in lines)
+
+
+def test_adam_matches_reference_update_rule_and_skips_nan():
+    import smnngp_b200 as sm
+    from smnngp_b200.spax import Adam, ConstraintTrainVar, positive
+    v = ConstraintTrainVar(1.5, constraint=positive())
+    raw0 = float(v.value)
+    opt = Adam({"v": v})
+    opt(0.1, {"v": 2.0})
+    # first Adam step moves by lr * sign(g) (bias-corrected m / sqrt(v) = 1)
+    assert abs(float(v.value) - (raw0 - 0.1)) <= 1e-6
+    opt(0.1, {"v": float("nan")})
+    assert abs(float(v.value) - (raw0 - 0.1)) <= 1e-6 and opt.step == 1
+    g = float(positive().grad(v.value))
+    h = 1e-6
+    assert abs(g - (float(positive()(v.value + h)) - float(positive()(v.value - h))) / (2 * h)) <= 1e-8
