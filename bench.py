@@ -20,6 +20,20 @@ import sys
 import threading
 import time
 
+
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["reference"] or "--impl=reference" in sys.argv:
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the reference arm is a CPU measurement on rank 0
+    # with every host core, so the thread pools are sized BEFORE NumPy / OpenBLAS / the OpenMP runtime are loaded
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(_host_cores())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -30,6 +44,16 @@ UNIT = "TFLOP/s"
 HP = dict(w_std=1.0, b_std=1e-8, last_w_std=1.0, eps=1e-6, alpha=2.0, beta=2.0)   # regression/train.py:37-45
 NUM_HIDDENS = 3
 CPU_SAMPLE_N = 20000
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from an `ncu --set full` capture.
+# It is NOT measured by this run (nothing is timed under a profiler): the capture it comes from, the launch it
+# belongs to and that launch's algorithmic bytes are named so the figure can be compared like for like.
+TRAFFIC = {"traffic": 2.644e9,
+           "traffic_launch": "potrf N=16384, first outer trailing update (n=15872, K=512): 1.29e11 flop, algorithmic "
+                             "bytes 2.08e9 (C lower tiles read+write 8 n (n+1) + panel 8 n K) - a different launch than "
+                             "the ones timed here (round-1 capture)",
+           "traffic_source": "profiles/r01_update_tma_ncu_summary.txt"}
 
 
 def lml_flops(n, d):
@@ -112,27 +136,62 @@ def host_threads():
     return max(n, 1), os.cpu_count()
 
 
+def _c3_golden(n, d):
+    """tests/golden/c3_full.json: losses recorded for the exact bench workload (N, D, seed 10, reference defaults)"""
+    path = os.path.join(ROOT, "tests", "golden", "c3_full.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        g = json.load(f)
+    return g if (g.get("n"), g.get("d")) == (n, d) else None
+
+
+def workload_config(n, d):
+    """`config` of BOTH arms (the reference arm runs a bounded sample of this same workload and says so in
+    cpu_baseline.sample): one function so the two dictionaries cannot drift apart."""
+    return {"workload": f"C3 NNGP Gram+Cholesky+Student-t LML, N={n} D={d} L=3 relu, eps=1e-6 a=b=2; CPU arms "
+                        f"(--impl reference, cpu_baseline) time the first {min(n, CPU_SAMPLE_N)} rows of the same "
+                        f"inputs, same_config_check holds the GPU time on exactly those rows",
+            "algorithmic_flops_per_step": lml_flops(n, d),
+            "l2": "working set 8*N^2 B >> 126 MB L2 (inputs larger than L2, no explicit flush)"}
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement on a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    try:                        # belt and braces for pools that were sized before our environment override
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=_host_cores())
+    except Exception:
+        pass
     n, d = min(args.n, CPU_SAMPLE_N), args.d
-    x, y = make_inputs(n, d)
-    for _ in range(args.warmup):
+    x, y = make_inputs(args.n, d)
+    x, y = x[:n], y[:n]                                  # the SAME rows the GPU arm's same_config_check evaluates
+    # W warm-up + K timed steps, bounded to ~4 min of wall clock in total: the first warm-up step calibrates, the
+    # remaining warm-ups and the number of timed steps shrink if (W + K) steps would not fit (reported as `steps`)
+    budget_s = 240.0
+    t_first, _ = cpu_port_step(x, y)
+    fit = max(1, int(budget_s / max(t_first, 1e-3)) - 1)
+    n_warm = max(0, min(args.warmup - 1, fit - 1))
+    for _ in range(n_warm):
         cpu_port_step(x, y)
-    times = [cpu_port_step(x, y)[0] for _ in range(args.steps)]
+    k_timed = max(1, min(args.steps, fit - n_warm))
+    res = [cpu_port_step(x, y) for _ in range(k_timed)]
+    times, loss = [r[0] for r in res], float(res[-1][1])
     t = float(np.mean(times))
     val = lml_flops(n, d) / t * 1e-12
     blas_threads, cores = host_threads()
     sample = (f"first {n} of the {args.n} rows of the same synthetic workload (D={d}, L=3 ReLU, Student-t LML); "
               f"the full N would need ~{(args.n / n) ** 3 * t / 60:.0f} min of CPU time")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "steps": k_timed, "warmup": n_warm + 1, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C3 NNGP Gram+Cholesky+Student-t LML, N={args.n} D={d} L=3 relu (CPU sample N={n})"},
+            "config": workload_config(args.n, d), "loss_on_sample": loss,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": blas_threads, "host_cpus": cores, "kind": "port",
-                             "sample": sample},
+                             "sample": sample, "seconds": t},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -265,9 +324,7 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "tma_gemm_kernel<EpiSubTma> (Cholesky trailing update C -= P P^T; TMA-fed persistent DMMA.8x8x4)",
                 "achieved": achieved, "peak": peak, "unit": UNIT,
                 "frac": (achieved / peak) if achieved else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
-                # (potrf N=16384, first trailing update, 1.29e11 flop, 2.08e9 algorithmic bytes):
-                "traffic": 2.644e9, "traffic_source": "profiles/r01_update_tma_ncu_summary.txt",
+                **TRAFFIC,
                 "launches_timed": int(n_upd), "kernel_ms_per_step": upd_ms.value / args.steps,
                 "scope": "rank 0's GPU (per-GPU rate against the per-GPU peak)",
                 "peak_source": "register-resident DMMA.8x8x4 issue-rate probe run live on this GPU "
@@ -298,29 +355,75 @@ def run_ours(args):
         except Exception as e:                                   # e.g. not enough memory for 16 N^2 bytes
             grad = {"error": repr(e)}
 
-    # ---- CPU baseline: the oracle port on a bounded sample, rank 0, N = 1 only ----
-    cpu = None
+    # ---- the SAME rows the CPU arms time (first CPU_SAMPLE_N rows), on the GPU: like-for-like time + parity ----
+    ns = min(n, CPU_SAMPLE_N)
+    xs, ys = x_np[:ns], y_np[:ns]
+    same_cfg, gpu_loss_s = None, None
+    if world == 1:
+        sm.device.release_workspaces()
+        torch.cuda.empty_cache()
+        xsd, ysd = torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev)
+        for _ in range(3):
+            o_s, _ = sm.device.lml(xsd, ysd, spec=spec, hp=hp_dev, kind="student_t")
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(5):
+            o_s, _ = sm.device.lml(xsd, ysd, spec=spec, hp=hp_dev, kind="student_t")
+        s1.record()
+        torch.cuda.synchronize()
+        gpu_loss_s = float(o_s[1].item())
+        ms_dev = s0.elapsed_time(s1) / 5
+        hp_np = np.array([HP[k] for k in ("w_std", "b_std", "last_w_std", "eps", "alpha", "beta")])
+        sm.device.lml(xs, ys, spec=spec, hp=hp_np, kind="student_t")            # host entry point warm-up (arena)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            sm.device.lml(xs, ys, spec=spec, hp=hp_np, kind="student_t")
+        ms_host = (time.perf_counter() - t0) / 3 * 1e3
+        same_cfg = {"n": ns, "d": d, "gpu_ms_device_resident": ms_dev, "gpu_ms_host_buffers": ms_host,
+                    "gpu_tflops_host_buffers": lml_flops(ns, d) / (ms_host * 1e-3) * 1e-12,
+                    "what": "our arm on exactly the rows / problem size the CPU arms (cpu_baseline, --impl reference) "
+                            "time; gpu_ms_host_buffers goes through smnngp_lml_host_f64 with H2D / D2H inside"}
+        del xsd, ysd
+        sm.device.release_workspaces()
+        torch.cuda.empty_cache()
+
+    # ---- CPU baseline: the oracle port on a bounded sample, rank 0, N = 1 only; its loss is the parity check ----
+    cpu, parity = None, None
     if world == 1 and not args.no_cpu_baseline:
-        ns = min(n, CPU_SAMPLE_N)
-        xs, ys = x_np[:ns], y_np[:ns]
-        t_cpu, _ = cpu_port_step(xs, ys)
+        t_cpu, loss_cpu = cpu_port_step(xs, ys)
         blas_threads, cores = host_threads()
         cpu = {"value": lml_flops(ns, d) / t_cpu * 1e-12, "unit": UNIT, "cores": blas_threads, "host_cpus": cores,
                "kind": "port", "seconds": t_cpu,
                "sample": f"first {ns} of the {n} rows of the same inputs (full N extrapolates to "
                          f"~{(n / ns) ** 3 * t_cpu / 60:.0f} min)"}
+        parity = {"n": ns, "oracle_loss": float(loss_cpu), "gpu_loss": gpu_loss_s,
+                  "rel_err": abs(gpu_loss_s - float(loss_cpu)) / abs(float(loss_cpu)), "tolerance": 1e-8,
+                  "what": "SPR.loss of the CUDA path vs the CPU oracle on the same rows, same hyper-parameters"}
+        same_cfg["cpu_ms"] = t_cpu * 1e3
+        same_cfg["speedup_host_buffers"] = t_cpu * 1e3 / same_cfg["gpu_ms_host_buffers"]
+    # full-size golden values: the oracle evaluated ONCE at the full C3 size (tests/golden/make_c3_golden.py) and the
+    # 1-GPU loss every multi-GPU run must reproduce
+    gold = _c3_golden(n, d)
+    if gold is not None:
+        parity = dict(parity or {})
+        if gold.get("oracle_loss") is not None:
+            parity["full_n_oracle_loss"] = gold["oracle_loss"]
+            parity["full_n_rel_err"] = abs(loss - gold["oracle_loss"]) / abs(gold["oracle_loss"])
+        if gold.get("gpu1_loss") is not None:
+            parity["vs_1gpu_rel_err"] = abs(loss - gold["gpu1_loss"]) / abs(gold["gpu1_loss"])
+            if world > 1 and not parity["vs_1gpu_rel_err"] <= 1e-12:
+                raise AssertionError(f"multi-GPU loss {loss!r} differs from the recorded 1-GPU loss {gold['gpu1_loss']!r}")
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C3 NNGP Gram+Cholesky+Student-t LML, N={n} D={d} L=3 relu, eps=1e-6 a=b=2",
-                       "algorithmic_flops_per_step": flops,
-                       "l2": "working set 8*N^2 B >> 126 MB L2 (inputs larger than L2, no explicit flush)",
-                       "parallelism": "1 GPU fused call" if world == 1 else
-                       f"block-row cyclic over {world} GPUs, panel exchange: " +
-                       ("NVLink peer stores (CUDA IPC)" if solver.exchange == "peer" else "NCCL broadcast + all-gather")},
+            "config": workload_config(n, d),
+            "parallelism": "1 GPU fused call" if world == 1 else
+            f"block-row cyclic over {world} GPUs, panel exchange: " +
+            ("NVLink peer stores (CUDA IPC)" if solver.exchange == "peer" else "NCCL broadcast + all-gather"),
             "loss": loss, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": cpu, "value_and_gradient": grad}
+            "cpu_baseline": cpu, "parity": parity, "same_config_check": same_cfg, "value_and_gradient": grad}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

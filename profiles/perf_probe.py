@@ -38,6 +38,34 @@ if "potrf" in which:
             print(f"potrf N={n} nb={nb}: {t:9.3f} ms  {n**3/3/t*1e-9:7.2f} TFLOP/s", flush=True)
         del a
     sm.device.set_panel_width(0)
+if "cusolver" in which:
+    # library bar on the same GPU: cuSOLVER Dpotrf through torch.linalg.cholesky_ex (lower), same SPD matrix as above
+    torch.backends.cuda.preferred_linalg_library("cusolver")
+    for n in [int(v) for v in os.environ.get("CUSOLVER_N", "8192,16384,32768,60000").split(",")]:
+        a = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+        out = torch.empty_like(a)
+        info = torch.empty((), dtype=torch.int32, device="cuda")
+        def base():
+            a.zero_(); a.diagonal().fill_(float(n)); a[:, 0] = 1.0; a[0, :] = 1.0; a[0, 0] = float(n)
+        def run():
+            base()
+            torch.linalg.cholesky_ex(a, upper=False, out=(out, info))
+        t = timed(run) - timed(base)
+        print(f"cusolver Dpotrf (torch.linalg.cholesky_ex) N={n}: {t:9.3f} ms  {n**3/3/t*1e-9:7.2f} TFLOP/s", flush=True)
+        del a, out
+        torch.cuda.empty_cache()
+if "potrf60k" in which:
+    n = 60000
+    a = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+    def run():
+        a.zero_(); a.diagonal().fill_(float(n)); a[:, 0] = 1.0; a[0, 0] = float(n)
+        sm.device.potrf_(a)
+    def base():
+        a.zero_(); a.diagonal().fill_(float(n)); a[:, 0] = 1.0; a[0, 0] = float(n)
+    t = timed(run) - timed(base)
+    print(f"potrf N={n}: {t:9.3f} ms  {n**3/3/t*1e-9:7.2f} TFLOP/s", flush=True)
+    del a
+    torch.cuda.empty_cache()
 if "gram" in which:
     for (n, d) in ((20000, 784), (10000, 8), (20000, 3072)):
         x = torch.from_numpy(pixel_data(n, d)[0]).cuda()

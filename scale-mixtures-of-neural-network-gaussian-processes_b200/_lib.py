@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsmnngp.so")
-SOURCES = ["gram.cu", "chol.cu", "reduce.cu", "api.cu", "stages.cu", "draws.cu", "grad.cu", "peer.cu", "exchange.cu"]
+SOURCES = ["gram.cu", "chol.cu", "reduce.cu", "api.cu", "stages.cu", "draws.cu", "grad.cu", "peer.cu", "exchange.cu",
+           "context.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets"]
 
@@ -55,31 +56,46 @@ def _stale():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into lib/libsmnngp.so (cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into lib/libsmnngp.so (cross-compiles without a GPU).  Safe to call from every
+    rank of a torchrun job at once: an exclusive file lock serialises the builders, the staleness check is repeated
+    under the lock (only the first rank compiles) and the library is moved into place atomically."""
     if not force and not _stale():
         return LIB_PATH
+    import fcntl
     nvcc = _nvcc()
     os.makedirs(LIB_DIR, exist_ok=True)
     obj_dir = os.path.join(_HERE, "build")
     os.makedirs(obj_dir, exist_ok=True)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB_PATH
 
-    def cc(src):
-        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("SMNNGP_NVCC_FLAGS", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
-        if verbose:
-            print(r.stderr)
-        return obj
+            def cc(src):
+                obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+                cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("SMNNGP_NVCC_FLAGS", "").split(), "-c",
+                       os.path.join(CSRC, src), "-o", obj]
+                if verbose:
+                    cmd.insert(1, "-Xptxas=-v")
+                r = subprocess.run(cmd, capture_output=True, text=True)
+                if r.returncode != 0:
+                    raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+                if verbose:
+                    print(r.stderr)
+                return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(cc, SOURCES))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart"], capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+            with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+                objs = list(ex.map(cc, SOURCES))
+            tmp = LIB_PATH + f".tmp{os.getpid()}"
+            # the -gencode on the link line keeps nvcc's device-link stub at sm_100a too (default: sm_52)
+            r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *objs,
+                                "-lcudart"], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+            os.replace(tmp, LIB_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

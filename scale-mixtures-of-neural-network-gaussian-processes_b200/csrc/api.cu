@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 
+#include "context.cuh"
 #include "kernels.cuh"
 
 using namespace smnngp;
@@ -13,7 +14,6 @@ using namespace smnngp;
 namespace {
 
 thread_local std::string g_err;
-int g_panel_width = 0;
 
 int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
   char buf[512];
@@ -46,7 +46,8 @@ struct Carver {
 inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
 int pick_nb(long long N) {
-  if (g_panel_width > 0) return g_panel_width;
+  const int pw = dctx().panel_width;
+  if (pw > 0) return pw;
   if (N >= 8192) return 512;
   if (N >= 2048) return 256;
   return 128;
@@ -121,21 +122,15 @@ cudaError_t enqueue_cross_gram(cudaStream_t s, const double* X1, long long N, co
   return launch_gram(s, g);
 }
 
-// grow-only device arena for the *_host_f64 entry points
-struct HostArena {
-  void* dev = nullptr;
-  size_t bytes = 0;
-  cudaStream_t stream = nullptr;
-} g_arena;
-
-int arena_reserve(size_t bytes) {
-  if (!g_arena.stream) CU(cudaStreamCreateWithFlags(&g_arena.stream, cudaStreamNonBlocking));
-  if (bytes <= g_arena.bytes) return SMNNGP_OK;
-  if (g_arena.dev) CU(cudaFree(g_arena.dev));
-  g_arena.dev = nullptr;
-  g_arena.bytes = 0;
-  CU(cudaMalloc(&g_arena.dev, bytes));
-  g_arena.bytes = bytes;
+// grow-only device arena of the *_host_f64 entry points: owned by the device context (context.cuh)
+int arena_reserve(DeviceCtx& c, size_t bytes) {
+  if (!c.arena_stream) CU(cudaStreamCreateWithFlags(&c.arena_stream, cudaStreamNonBlocking));
+  if (bytes <= c.arena_bytes) return SMNNGP_OK;
+  if (c.arena) CU(cudaFree(c.arena));
+  c.arena = nullptr;
+  c.arena_bytes = 0;
+  CU(cudaMalloc(&c.arena, bytes));
+  c.arena_bytes = bytes;
   return SMNNGP_OK;
 }
 
@@ -145,7 +140,7 @@ extern "C" {
 
 int smnngp_abi_version(void) { return SMNNGP_ABI_VERSION; }
 const char* smnngp_last_error(void) { return g_err.c_str(); }
-void smnngp_set_panel_width(int nb) { g_panel_width = nb > 0 ? (nb + PB - 1) / PB * PB : 0; }
+void smnngp_set_panel_width(int nb) { dctx().panel_width = nb > 0 ? (nb + PB - 1) / PB * PB : 0; }
 
 void smnngp_set_tile_variant(int v) { tile_variant() = (v >= 0 && v <= 2) ? v : 0; }
 int smnngp_debug_occupancy(int variant) { return debug_gemm_occupancy(variant); }
@@ -187,6 +182,7 @@ int smnngp_gram_f64(void* stream, const double* X, const double* X2, int64_t N, 
                     int n_hidden, int act, int arch, const double* hp_dev, int shift, int out_mode,
                     double* K_out, int64_t ld, void* workspace, size_t workspace_bytes) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   const bool sym = (X2 == nullptr || X2 == X);
   if (sym) M = N;
   if (!X || !K_out || !hp_dev || N < 0 || M < 0 || D <= 0 || ld < M || !valid_stack(n_hidden, act, arch) ||
@@ -213,6 +209,7 @@ int smnngp_gram_f64(void* stream, const double* X, const double* X2, int64_t N, 
 int smnngp_nngp_diag_f64(void* stream, const double* X, int64_t N, int64_t D, int n_hidden, int act, int arch,
                          const double* hp_dev, double* q_out, void* workspace, size_t workspace_bytes) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!X || !q_out || !hp_dev || N < 0 || D <= 0 || !valid_stack(n_hidden, act, arch) || N > INT32_MAX)
     return fail(SMNNGP_EINVAL, "smnngp_nngp_diag_f64: invalid argument");
   if (N == 0) return SMNNGP_OK;
@@ -237,6 +234,7 @@ size_t smnngp_potrf_workspace_bytes(int64_t N) {
 int smnngp_potrf_trapezoid_f64(void* stream, double* A, int64_t M, int64_t N, int64_t ld, double* logdet_dev,
                                int* info_dev, void* workspace, size_t workspace_bytes) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!A || N < 0 || M < N || ld < N || !info_dev || M > INT32_MAX)
     return fail(SMNNGP_EINVAL, "smnngp_potrf_trapezoid_f64: invalid argument");
   Carver c(workspace);
@@ -284,6 +282,7 @@ __global__ void scale_shift_copy_kernel(const double* __restrict__ src, long lon
 int smnngp_cov_solve_f64(void* stream, const double* cov, int64_t N, int64_t ld, const double* y, double scale,
                          double shift, void* workspace, size_t workspace_bytes, double* out_dev, int* info_dev) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!cov || !y || !out_dev || !info_dev || N <= 0 || ld < N || N + 1 > 65535)
     return fail(SMNNGP_EINVAL, "smnngp_cov_solve_f64: invalid argument (N must be < 65535 on this entry point)");
   Carver c(workspace);
@@ -319,6 +318,7 @@ int smnngp_lml_f64(void* stream, const double* X, const double* y, int64_t N, in
                    int arch, const double* hp_dev, int kind, void* workspace, size_t workspace_bytes,
                    double* out_dev, int* info_dev) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!X || !y || !hp_dev || !out_dev || !info_dev || N <= 0 || D <= 0 || !valid_stack(n_hidden, act, arch) ||
       (kind != KIND_GAUSS && kind != KIND_STUDENT_T) || N + 1 > INT32_MAX || D > INT32_MAX)
     return fail(SMNNGP_EINVAL, "smnngp_lml_f64: invalid argument");
@@ -374,6 +374,7 @@ int smnngp_lml_grad_f64(void* stream, const double* X, const double* y, int64_t 
                         int arch, const double* hp_dev, int kind, void* workspace, size_t workspace_bytes,
                         double* out_dev, double* grad_dev, int* info_dev) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!X || !y || !hp_dev || !out_dev || !grad_dev || !info_dev || N <= 0 || D <= 0 ||
       !valid_stack(n_hidden, act, arch) || (kind != KIND_GAUSS && kind != KIND_STUDENT_T) ||
       2 * N + 1 > INT32_MAX || D > INT32_MAX)
@@ -460,6 +461,7 @@ int smnngp_predict_f64(void* stream, const double* X, const double* Y, const dou
                        void* workspace, size_t workspace_bytes, double* mean_out, double* var_out,
                        int* info_dev) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!X || !Y || !Xt || !hp_dev || !mean_out || !var_out || !info_dev || N <= 0 || T <= 0 || C <= 0 || D <= 0 ||
       !valid_stack(n_hidden, act, arch) || shift < 0 || shift > 3 || N + T + C > INT32_MAX || D > INT32_MAX)
     return fail(SMNNGP_EINVAL, "smnngp_predict_f64: invalid argument");
@@ -477,6 +479,7 @@ int smnngp_predict_cov_f64(void* stream, const double* X, const double* Y, const
                            void* workspace, size_t workspace_bytes, double* mean_out, double* var_out,
                            double* cov_out, int64_t ld_cov, int* info_dev) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!X || !Y || !Xt || !hp_dev || !mean_out || !var_out || !cov_out || !info_dev || N <= 0 || T <= 0 || C <= 0 ||
       D <= 0 || ld_cov < T || !valid_stack(n_hidden, act, arch) || shift < 0 || shift > 3 ||
       N + T + C > INT32_MAX || D > INT32_MAX)
@@ -496,6 +499,7 @@ int smnngp_test_nll_f64(void* stream, const double* X, const double* y, const do
                         double* nll_out_dev, double* mean_out, double* var_out, double* logp_out,
                         int* info_dev) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!X || !y || !Xt || !yt || !hp_dev || !nll_out_dev || !info_dev || N <= 0 || T <= 0 || D <= 0 ||
       !valid_stack(n_hidden, act, arch) || (kind != KIND_GAUSS && kind != KIND_STUDENT_T) ||
       N + T + 1 > INT32_MAX || D > INT32_MAX)
@@ -531,6 +535,7 @@ int smnngp_test_nll_f64(void* stream, const double* X, const double* y, const do
 int smnngp_grid_base_f64(void* stream, const double* X, const double* Xt, int64_t N, int64_t T, int64_t D,
                          double* K0dd, int64_t ld0, double* K0td, int64_t ld0t, double* q_d, double* q_t) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!X || !K0dd || !q_d || N <= 0 || D <= 0 || ld0 < N || T < 0 || (T > 0 && (!Xt || !K0td || !q_t || ld0t < N)) ||
       N > INT32_MAX || T > INT32_MAX || D > INT32_MAX)
     return fail(SMNNGP_EINVAL, "smnngp_grid_base_f64: invalid argument");
@@ -555,6 +560,7 @@ int smnngp_grid_point_f64(void* stream, const double* K0dd, int64_t ld0, const d
                           int act, int arch, const double* hp_dev, void* workspace, size_t workspace_bytes,
                           double* mean_out, double* var_out, double* out_dev, int* info_dev) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!K0dd || !K0td || !q_d || !q_t || !y || !hp_dev || !mean_out || !var_out || !out_dev || !info_dev || N <= 0 ||
       T <= 0 || ld0 < N || ld0t < N || !valid_stack(n_hidden, act, arch) || N + T + 1 > INT32_MAX)
     return fail(SMNNGP_EINVAL, "smnngp_grid_point_f64: invalid argument");
@@ -599,11 +605,13 @@ int smnngp_grid_point_f64(void* stream, const double* K0dd, int64_t ld0, const d
 // host-buffer entry points
 // ---------------------------------------------------------------------------------------------------------
 void smnngp_host_release(void) {
-  if (g_arena.dev) cudaFree(g_arena.dev);
-  g_arena.dev = nullptr;
-  g_arena.bytes = 0;
-  if (g_arena.stream) cudaStreamDestroy(g_arena.stream);
-  g_arena.stream = nullptr;
+  DeviceCtx& c = dctx();
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
+  if (c.arena) cudaFree(c.arena);
+  c.arena = nullptr;
+  c.arena_bytes = 0;
+  if (c.arena_stream) cudaStreamDestroy(c.arena_stream);
+  c.arena_stream = nullptr;
 }
 
 int smnngp_lml_host_f64(const double* X, const double* y, int64_t N, int64_t D, int n_hidden, int act, int arch,
@@ -613,16 +621,18 @@ int smnngp_lml_host_f64(const double* X, const double* y, int64_t N, int64_t D, 
   Carver c(nullptr);
   c.take<double>((size_t)N * D); c.take<double>(N); c.take<double>(HP_COUNT); c.take<double>(4); c.take<int>(1);
   const size_t io_bytes = c.total();
-  int rc = arena_reserve(io_bytes + ws_bytes);
+  Enter scope(nullptr);                       // host entry points run on the calling thread's current device
+  DeviceCtx& dc = *scope.ctx;
+  int rc = arena_reserve(dc, io_bytes + ws_bytes);
   if (rc != SMNNGP_OK) return rc;
-  Carver a(g_arena.dev);
+  Carver a(dc.arena);
   double* dX = a.take<double>((size_t)N * D);
   double* dy = a.take<double>(N);
   double* dhp = a.take<double>(HP_COUNT);
   double* dout = a.take<double>(4);
   int* dinfo = a.take<int>(1);
-  void* ws = static_cast<char*>(g_arena.dev) + io_bytes;
-  cudaStream_t s = g_arena.stream;
+  void* ws = static_cast<char*>(dc.arena) + io_bytes;
+  cudaStream_t s = dc.arena_stream;
   CU(cudaMemcpyAsync(dX, X, (size_t)N * D * 8, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(dy, y, (size_t)N * 8, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(dhp, hp, HP_COUNT * 8, cudaMemcpyHostToDevice, s));
@@ -645,17 +655,19 @@ int smnngp_lml_grad_host_f64(const double* X, const double* y, int64_t N, int64_
   c.take<double>((size_t)N * D); c.take<double>(N); c.take<double>(HP_COUNT); c.take<double>(4);
   c.take<double>(HP_COUNT); c.take<int>(1);
   const size_t io_bytes = c.total();
-  int rc = arena_reserve(io_bytes + ws_bytes);
+  Enter scope(nullptr);                       // host entry points run on the calling thread's current device
+  DeviceCtx& dc = *scope.ctx;
+  int rc = arena_reserve(dc, io_bytes + ws_bytes);
   if (rc != SMNNGP_OK) return rc;
-  Carver a(g_arena.dev);
+  Carver a(dc.arena);
   double* dX = a.take<double>((size_t)N * D);
   double* dy = a.take<double>(N);
   double* dhp = a.take<double>(HP_COUNT);
   double* dout = a.take<double>(4);
   double* dgrad = a.take<double>(HP_COUNT);
   int* dinfo = a.take<int>(1);
-  void* ws = static_cast<char*>(g_arena.dev) + io_bytes;
-  cudaStream_t s = g_arena.stream;
+  void* ws = static_cast<char*>(dc.arena) + io_bytes;
+  cudaStream_t s = dc.arena_stream;
   CU(cudaMemcpyAsync(dX, X, (size_t)N * D * 8, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(dy, y, (size_t)N * 8, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(dhp, hp, HP_COUNT * 8, cudaMemcpyHostToDevice, s));
@@ -680,9 +692,11 @@ int smnngp_predict_host_f64(const double* X, const double* Y, const double* Xt, 
   c.take<double>((size_t)N * D); c.take<double>((size_t)N * C); c.take<double>((size_t)T * D);
   c.take<double>(HP_COUNT); c.take<double>((size_t)T * C); c.take<double>(T); c.take<int>(1);
   const size_t io_bytes = c.total();
-  int rc = arena_reserve(io_bytes + ws_bytes);
+  Enter scope(nullptr);                       // host entry points run on the calling thread's current device
+  DeviceCtx& dc = *scope.ctx;
+  int rc = arena_reserve(dc, io_bytes + ws_bytes);
   if (rc != SMNNGP_OK) return rc;
-  Carver a(g_arena.dev);
+  Carver a(dc.arena);
   double* dX = a.take<double>((size_t)N * D);
   double* dY = a.take<double>((size_t)N * C);
   double* dXt = a.take<double>((size_t)T * D);
@@ -690,8 +704,8 @@ int smnngp_predict_host_f64(const double* X, const double* Y, const double* Xt, 
   double* dmean = a.take<double>((size_t)T * C);
   double* dvar = a.take<double>(T);
   int* dinfo = a.take<int>(1);
-  void* ws = static_cast<char*>(g_arena.dev) + io_bytes;
-  cudaStream_t s = g_arena.stream;
+  void* ws = static_cast<char*>(dc.arena) + io_bytes;
+  cudaStream_t s = dc.arena_stream;
   CU(cudaMemcpyAsync(dX, X, (size_t)N * D * 8, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(dY, Y, (size_t)N * C * 8, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(dXt, Xt, (size_t)T * D * 8, cudaMemcpyHostToDevice, s));
@@ -719,9 +733,11 @@ int smnngp_test_nll_host_f64(const double* X, const double* y, const double* Xt,
   c.take<double>((size_t)N * D); c.take<double>(N); c.take<double>((size_t)T * D); c.take<double>(T);
   c.take<double>(HP_COUNT); c.take<double>(T); c.take<double>(T); c.take<double>(1); c.take<int>(1);
   const size_t io_bytes = c.total();
-  int rc = arena_reserve(io_bytes + ws_bytes);
+  Enter scope(nullptr);                       // host entry points run on the calling thread's current device
+  DeviceCtx& dc = *scope.ctx;
+  int rc = arena_reserve(dc, io_bytes + ws_bytes);
   if (rc != SMNNGP_OK) return rc;
-  Carver a(g_arena.dev);
+  Carver a(dc.arena);
   double* dX = a.take<double>((size_t)N * D);
   double* dy = a.take<double>(N);
   double* dXt = a.take<double>((size_t)T * D);
@@ -731,8 +747,8 @@ int smnngp_test_nll_host_f64(const double* X, const double* y, const double* Xt,
   double* dvar = a.take<double>(T);
   double* dnll = a.take<double>(1);
   int* dinfo = a.take<int>(1);
-  void* ws = static_cast<char*>(g_arena.dev) + io_bytes;
-  cudaStream_t s = g_arena.stream;
+  void* ws = static_cast<char*>(dc.arena) + io_bytes;
+  cudaStream_t s = dc.arena_stream;
   CU(cudaMemcpyAsync(dX, X, (size_t)N * D * 8, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(dy, y, (size_t)N * 8, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(dXt, Xt, (size_t)T * D * 8, cudaMemcpyHostToDevice, s));

@@ -6,6 +6,7 @@
 // Rows below the square part (the trapezoid) are carried through TRSM + update, so appended rows y^T and K_td
 // come out as (L^-1 y)^T and (L^-1 K_dt)^T: the triangular solves of spax/utils.py:180 and of cho_solve are
 // fused into the factorisation and run on the tensor pipe.
+#include "context.cuh"
 #include "gemm_core.cuh"
 #include "kernels.cuh"
 #include "tma_core.cuh"
@@ -151,14 +152,8 @@ cudaError_t launch_gemm_cfg(cudaStream_t s, const GemmParams& p) {
   bool a16 = (p.lda % 2 == 0) && (p.ldb % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
   auto kern = a16 ? gemm_kernel<Cfg, true, EPI> : gemm_kernel<Cfg, false, EPI>;
-  static bool configured[2] = {false, false};
-  if (!configured[a16]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e != cudaSuccess) return e;
-    configured[a16] = true;
-  }
+  cudaError_t e = configure_kernel_once(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, true);
+  if (e != cudaSuccess) return e;
   kern<<<(unsigned)tiles, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
   instr().launches++;
   return cudaGetLastError();
@@ -482,15 +477,9 @@ cudaError_t launch_gemm_store_lower(cudaStream_t s, const GemmParams& p) {
   return launch_gemm_cfg<TilePair, EPI_STORE>(s, p);
 }
 
-long long*& potf2_clock_buffer() {
-  static long long* p = nullptr;
-  return p;
-}
-
 cudaError_t launch_potf2_trtri(cudaStream_t s, double* A, long long lda, int w, double* Linv, double* logdet,
                                int* info, int global_col0) {
-  cudaError_t e = cudaFuncSetAttribute(potf2_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       PF_SMEM_BYTES);
+  cudaError_t e = configure_kernel_once(reinterpret_cast<const void*>(potf2_trtri_kernel), PF_SMEM_BYTES, false);
   if (e != cudaSuccess) return e;
   potf2_trtri_kernel<<<1, PF_THREADS, PF_SMEM_BYTES, s>>>(A, lda, w, Linv, logdet, info, global_col0, potf2_clock_buffer());
   instr().launches++;
@@ -571,39 +560,21 @@ static cudaError_t potrf_serial(cudaStream_t s, double* A, long long lda, long l
 // update kernel would otherwise hold every SM, so for trailing matrices small enough that the chain matters
 // update_b leaves a few SMs free.
 namespace {
-struct LookaheadCtx {
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_diag = nullptr, ev_a = nullptr;
-  bool ok = false;
-};
-LookaheadCtx g_la[64];
-
-LookaheadCtx* lookahead_ctx() {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  LookaheadCtx& c = g_la[dev];
-  if (!c.ok) {
+// side stream + events of the current device's context (context.cuh), created on first use
+DeviceCtx* lookahead_ctx() {
+  DeviceCtx& c = dctx();
+  if (!c.la_ok) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&c.ev_diag, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&c.ev_a, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    c.ok = true;
+    c.la_ok = true;
   }
   return &c;
 }
 }  // namespace
-
-int& lookahead_mode() {
-  static int v = 1;
-  return v;
-}
-// SMs the bulk update leaves to the look-ahead chain: [0] trailing matrix < 24000 columns, [1] larger
-int* lookahead_reserve() {
-  static int v[2] = {8, 0};
-  return v;
-}
 
 cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long Mfull, long long N, int NB,
                             double* Linv_base, double* logdet, int* info, long long linv_stride,
@@ -611,7 +582,7 @@ cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long 
   if (NB < PB) NB = PB;
   NB = (NB / PB) * PB;
   if (NB > LINV_BLOCKS * PB) NB = LINV_BLOCKS * PB;
-  LookaheadCtx* la = (lookahead_mode() != 0 && linv_stride == 0 && N > NB) ? lookahead_ctx() : nullptr;
+  DeviceCtx* la = (lookahead_mode() != 0 && linv_stride == 0 && N > NB) ? lookahead_ctx() : nullptr;
   if (la == nullptr)
     return potrf_serial(s, A, lda, Mfull, N, NB, Linv_base, logdet, info, linv_stride, 0, true, ident_row0);
 

@@ -17,6 +17,7 @@
 #include "../../include/smnngp.h"
 
 #include "gemm_core.cuh"
+#include "context.cuh"
 #include "kernels.cuh"
 #include "tma_core.cuh"
 
@@ -183,16 +184,14 @@ __global__ void stage_diag_kernel(const double* __restrict__ A, long long lda, i
 // cuStreamWaitValue64: the wait is executed by the stream's front-end, no SM is occupied while waiting
 typedef CUresult (*PFN_streamWaitValue64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
 PFN_streamWaitValue64 stream_wait_fn() {
-  static PFN_streamWaitValue64 fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static const PFN_streamWaitValue64 fn = []() -> PFN_streamWaitValue64 {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_streamWaitValue64>(p);
-  }
+      return reinterpret_cast<PFN_streamWaitValue64>(p);
+    return nullptr;
+  }();
   return fn;
 }
 int& wait_mode() {
@@ -223,6 +222,7 @@ extern "C" {
 int smnngp_stage_factor_diag_inv_f64(void* stream, const double* A, int64_t lda, int64_t w, double* T,
                                      double* linv_ws, double* logdet_dev, int* info_dev, int64_t gcol0) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!A || !T || !linv_ws || !logdet_dev || !info_dev || w <= 0 || w > LINV_BLOCKS * PB) return SMNNGP_EINVAL;
   (void)gcol0;
   stage_diag_kernel<<<(unsigned)(2 * w), 128, 0, s>>>(A, lda, (int)w, T, w);
@@ -238,6 +238,7 @@ int smnngp_stage_scatter_inverse_f64(void* stream, const double* Ut, int64_t ldu
                                      int P, int64_t ldw, void* const* flag_ptrs, int64_t flag_index, uint64_t seq,
                                      unsigned int* counter) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!Ut || !dst_ptrs || !flag_ptrs || !counter || P < 1 || P > MAX_PEERS || w <= 0) return SMNNGP_EINVAL;
   ScatterParams sp{};
   sp.P = P;
@@ -251,6 +252,7 @@ int smnngp_stage_scatter_inverse_f64(void* stream, const double* Ut, int64_t ldu
 
 int smnngp_stage_signal_f64(void* stream, void* const* flag_ptrs, int P, int64_t flag_index, uint64_t seq) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!flag_ptrs || P < 1 || P > MAX_PEERS) return SMNNGP_EINVAL;
   PeerSignal sg{};
   fill_signal(sg, flag_ptrs, P, flag_index, seq, nullptr);
@@ -262,6 +264,7 @@ int smnngp_stage_signal_f64(void* stream, void* const* flag_ptrs, int P, int64_t
 int smnngp_stage_wait_flags_f64(void* stream, const void* flags_local, int64_t first, int count, uint64_t seq,
                                 double timeout_s, int* info_dev) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!flags_local || count < 0) return SMNNGP_EINVAL;
   if (count == 0) return SMNNGP_OK;
   if (wait_mode() == 0 && stream_wait_fn() != nullptr) {
@@ -286,6 +289,7 @@ int smnngp_stage_push_panel_f64(void* stream, const double* Ploc, int64_t m, int
                                 int64_t local_row0, int64_t c1, int64_t n, void* const* peer_ptrs,
                                 void* const* flag_ptrs, int64_t flag_index, uint64_t seq) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!peer_ptrs || !flag_ptrs || P < 1 || P > MAX_PEERS || m < 0 || w != db || db <= 0 || rank < 0 || rank >= P ||
       (m > 0 && !Ploc) || local_row0 % db != 0)
     return SMNNGP_EINVAL;
@@ -326,6 +330,7 @@ int smnngp_stage_trsm_scatter_f64(void* stream, const double* R, int64_t ldr, in
                                   int64_t db, int64_t local_row0, int64_t c1, int64_t n, int64_t ld_peer,
                                   void* const* flag_ptrs, int64_t flag_index, uint64_t seq, unsigned int* counter) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!W || !peer_ptrs || !flag_ptrs || !counter || P < 1 || P > MAX_PEERS || m < 0 || w <= 0 ||
       db <= 0 || rank < 0 || rank >= P)
     return SMNNGP_EINVAL;

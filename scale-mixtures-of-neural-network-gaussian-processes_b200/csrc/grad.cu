@@ -270,9 +270,7 @@ cudaError_t launch_grad_fallback(cudaStream_t s, const GradParams& p) {
   using Cfg = TilePair;
   long long tiles = count_tiles<Cfg>(p.g.N, p.g.M, 1);
   auto kern = p.g.act == ACT_RELU ? grad_gram_kernel<Cfg, ALIGN16, ACT_RELU> : grad_gram_kernel<Cfg, ALIGN16, ACT_ERF>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaError_t e = configure_kernel_once(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, true);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)tiles, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
   instr().launches++;

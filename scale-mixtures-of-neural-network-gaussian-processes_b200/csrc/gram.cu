@@ -277,9 +277,7 @@ template <typename Cfg, bool ALIGN16>
 cudaError_t launch_gram_t(cudaStream_t s, const GramParams& p) {
   long long tiles = count_tiles<Cfg>(p.N, p.M, p.symmetric);
   auto kern = p.act == ACT_RELU ? gram_kernel<Cfg, ALIGN16, ACT_RELU> : gram_kernel<Cfg, ALIGN16, ACT_ERF>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaError_t e = configure_kernel_once(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, true);
   if (e != cudaSuccess) return e;
   kern<<<(unsigned)tiles, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
   instr().launches++;

@@ -187,11 +187,6 @@ cudaError_t launch_fill_nan_if_bad(cudaStream_t s, const int* info, double* buf,
 
 // ---- instrumentation ---------------------------------------------------------------------------------------
 namespace {
-Instrumentation g_instr;
-struct EvPair { cudaEvent_t a, b; };
-EvPair g_ev[4096];
-int g_ev_made = 0, g_ev_used = 0;
-
 template <int NACC>
 __global__ void dmma_peak_kernel(double* out, int iters, double seed) {
   double c[NACC][2];
@@ -210,48 +205,6 @@ __global__ void dmma_peak_kernel(double* out, int iters, double seed) {
   if (s == 123.456) out[0] = s;
 }
 }  // namespace
-
-Instrumentation& instr() { return g_instr; }
-
-int& tile_variant() {
-  static int v = 0;
-  return v;
-}
-
-void instr_reset() {
-  g_instr.launches = 0;
-  g_instr.update_flops = 0.0;
-  g_instr.update_alg_flops = 0.0;
-  g_ev_used = 0;
-}
-
-void instr_begin_update(cudaStream_t s, double alg_flops) {
-  if (g_ev_used >= 4096) return;
-  if (g_ev_used >= g_ev_made) {
-    cudaEventCreate(&g_ev[g_ev_made].a);
-    cudaEventCreate(&g_ev[g_ev_made].b);
-    g_ev_made++;
-  }
-  g_instr.update_alg_flops += alg_flops;
-  cudaEventRecord(g_ev[g_ev_used].a, s);
-}
-
-void instr_end_update(cudaStream_t s) {
-  if (g_ev_used >= g_ev_made) return;
-  cudaEventRecord(g_ev[g_ev_used].b, s);
-  g_ev_used++;
-}
-
-double instr_collect_update_ms(int* n_out) {
-  double total = 0.0;
-  for (int i = 0; i < g_ev_used; i++) {
-    cudaEventSynchronize(g_ev[i].b);
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, g_ev[i].a, g_ev[i].b) == cudaSuccess) total += ms;
-  }
-  if (n_out) *n_out = g_ev_used;
-  return total;
-}
 
 double dmma_peak_tflops(int sms) {
   double* d = nullptr;

@@ -5,6 +5,7 @@
 
 #include <string>
 
+#include "context.cuh"
 #include "kernels.cuh"
 
 using namespace smnngp;
@@ -18,6 +19,7 @@ extern "C" {
 int smnngp_stage_qtable_f64(void* stream, const double* X, int64_t N, int64_t D, int n_hidden, int act, int arch,
                             const double* hp_dev, double* tab, int64_t tab_ld, double* q, double* scal) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!X || !tab || !q || !hp_dev || N <= 0 || D <= 0) return SMNNGP_EINVAL;
   cudaError_t e = launch_qtable(s, X, D, (int)N, (int)D, n_hidden, act, arch, hp_dev, tab, tab_ld, q);
   if (e != cudaSuccess) return SMNNGP_ECUDA;
@@ -30,6 +32,7 @@ int smnngp_stage_gram_f64(void* stream, const double* X1, int64_t n1, const doub
                           int64_t tab_ld1, const double* tab2, int64_t tab_ld2, const double* scal, int shift,
                           int symmetric_lower, double* K, int64_t ldk) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!X1 || !X2 || !K || !hp_dev || !tab1 || !tab2 || n1 < 0 || n2 < 0 || D <= 0) return SMNNGP_EINVAL;
   GramParams g{};
   g.X1 = X1; g.X2 = X2; g.ld1 = D; g.ld2 = D; g.N = (int)n1; g.M = (int)n2; g.D = (int)D;
@@ -44,6 +47,7 @@ int smnngp_stage_gram_f64(void* stream, const double* X1, int64_t n1, const doub
 int smnngp_stage_factor_diag_f64(void* stream, double* A, int64_t lda, int64_t w, double* linv_blocks,
                                  double* logdet_dev, int* info_dev, int64_t gcol0) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!A || !linv_blocks || !logdet_dev || !info_dev || w <= 0) return SMNNGP_EINVAL;
   (void)gcol0;
   return fail_stage(potrf_trapezoid(s, A, lda, w, w, (int)((w + PB - 1) / PB * PB), linv_blocks, logdet_dev, info_dev,
@@ -54,6 +58,7 @@ int smnngp_stage_factor_diag_f64(void* stream, double* A, int64_t lda, int64_t w
 int smnngp_stage_trsm_f64(void* stream, double* R, int64_t ldr, int64_t m, int64_t w, const double* L, int64_t ldl,
                           const double* linv_blocks) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!R || !L || !linv_blocks || m < 0 || w <= 0) return SMNNGP_EINVAL;
   if (m == 0) return SMNNGP_OK;
   for (int64_t j0 = 0; j0 < w; j0 += PB) {
@@ -83,6 +88,7 @@ int smnngp_stage_update_f64(void* stream, const double* A, int64_t lda, const do
                             int64_t ldc, int64_t M, int64_t N, int64_t K, int lower, int64_t cyc_db, int64_t cyc_p,
                             int64_t base_shift, int sm_reserve) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
   if (!A || !B || !C || M < 0 || N < 0 || K <= 0) return SMNNGP_EINVAL;
   GemmParams u{};
   u.A = A; u.lda = lda; u.B = B; u.ldb = ldb; u.C = C; u.ldc = ldc;
@@ -111,6 +117,7 @@ int smnngp_stage_predict_finalize_f64(void* stream, const double* V, int64_t ldv
   if (!V || !Z || !ktt || !info_dev || !mean || !var || T < 0 || C <= 0 || N <= 0 || T > INT32_MAX || C > INT32_MAX)
     return SMNNGP_EINVAL;
   if (T == 0) return SMNNGP_OK;
+  Enter scope(static_cast<cudaStream_t>(stream));
   return fail_stage(launch_predict_finalize(static_cast<cudaStream_t>(stream), V, ldv, Z, ldz, ktt, (int)T, (int)C, N,
                                             info_dev, mean, var));
 }
@@ -123,6 +130,7 @@ int smnngp_stage_test_nll_finalize_f64(void* stream, const double* mean, const d
   if (!mean || !var || !ytest || !hp_dev || !info_dev || !nll_out_dev || T <= 0 || T > INT32_MAX ||
       (kind != KIND_GAUSS && kind != KIND_STUDENT_T) || (kind == KIND_STUDENT_T && !quad2_dev))
     return SMNNGP_EINVAL;
+  Enter scope(static_cast<cudaStream_t>(stream));
   return fail_stage(launch_test_nll_finalize(static_cast<cudaStream_t>(stream), mean, var, ytest, (int)T, N, y_mean,
                                              y_std, hp_dev, kind, quad2_dev ? quad2_dev : mean, info_dev, logp,
                                              nll_out_dev));
@@ -130,6 +138,7 @@ int smnngp_stage_test_nll_finalize_f64(void* stream, const double* mean, const d
 
 int smnngp_stage_sumsq_f64(void* stream, const double* z, int64_t n, double* out_dev) {
   if (!z || !out_dev || n < 0) return SMNNGP_EINVAL;
+  Enter scope(static_cast<cudaStream_t>(stream));
   return fail_stage(launch_sumsq(static_cast<cudaStream_t>(stream), z, n, out_dev));
 }
 
@@ -137,6 +146,7 @@ int smnngp_stage_sumsq_f64(void* stream, const double* z, int64_t n, double* out
 int smnngp_stage_lml_finalize_f64(void* stream, const double* sums_dev, const double* hp_dev, int kind, int64_t N,
                                   const int* info_dev, double* out_dev) {
   if (!sums_dev || !hp_dev || !info_dev || !out_dev) return SMNNGP_EINVAL;
+  Enter scope(static_cast<cudaStream_t>(stream));
   // lml_finalize reads scal[SC_LOGDET], scal[SC_QUAD]: present the two sums at those offsets
   return fail_stage(launch_lml_finalize(static_cast<cudaStream_t>(stream), sums_dev - SC_LOGDET, hp_dev, kind, N,
                                         info_dev, out_dev));

@@ -26,6 +26,8 @@
 
 namespace smnngp {
 
+cudaError_t configure_kernel_once(const void* fn, int smem_bytes, bool carveout);   // context.cu
+
 constexpr int TM_BM = 128, TM_BN = 64, TM_STAGES = 4;
 constexpr int TM_A_BYTES = TM_BM * BK * 8;                 // 16384
 constexpr int TM_B_BYTES = TM_BN * BK * 8;                 // 8192
@@ -46,6 +48,10 @@ struct TmaShape {
   // 1: operand B is LOWER triangular (row j zero right of column j), so the contraction of the tile whose first
   // column is c0 only runs over k < c0 + 64 (panel solve with the explicit inverse: rows * inv(L)^T)
   int k_upto_col;
+  // Always 0 (aggregate initialisation leaves it value-initialised).  The math warps AND it with a token derived from
+  // the fragments they loaded and add the result to the address of the stage-release arrive: ptxas cannot see the
+  // value of a kernel parameter, so the arrive carries a true data dependency on the loads (see tma_gemm_kernel).
+  unsigned int zero;
 };
 
 // Block-row-cyclic mask: number of column tiles of row tile ti that touch the active region (a prefix of the row,
@@ -91,16 +97,14 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline PFN_encodeTiled tma_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static const PFN_encodeTiled fn = []() -> PFN_encodeTiled {      // thread-safe one-time lookup (idempotent cache)
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
+      return reinterpret_cast<PFN_encodeTiled>(p);
+    return nullptr;
+  }();
   return fn;
 }
 
@@ -155,9 +159,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ uint32_t hi32(double v) { return (uint32_t)__double2hiint(v); }
 
 // optional Epi::finish(params): run once per CTA by the 256 math threads after the last tile (e.g. cross-GPU signal)
 template <class Epi, class = void>
@@ -232,7 +237,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t off0 = (uint32_t)((((4 * (j & 1)) ^ g8) << 4) | ((j >> 1) << 3));
   const uint32_t a_off = (uint32_t)((wm * 64 + g8) * 128) + off0;
   const uint32_t b_off = (uint32_t)(TM_A_BYTES + (wn * 32 + g8) * 128) + off0;
-  int s = 0, prev_stage = -1;
+  int s = 0;
   uint32_t ph = 0;
   TileCursor cur;
   for (long long t = 2ll * blockIdx.x + g; t < sh.tiles; t += stride) {
@@ -268,19 +273,24 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
           for (int ni = 0; ni < NI; ni++) dmma8x8x4(acc[mi][ni], a[cur][mi], b[cur][ni]);
       }
-      // Stage release is DELAYED BY ONE SLAB: ptxas is free to issue the mbarrier arrive right after the last
-      // ld.shared of a slab (before the DMMAs that consume the fragments), and a stage released while loads
-      // are still in flight was observed to be overwritten by the producer's next TMA (wrong fragments in ~0.3 %
-      // of the tiles).  Releasing slab k's stage at the end of slab k+1 puts a full slab of in-order DMMA issue
-      // - which cannot start before slab k's fragments have landed in registers - between load and release.
-      __syncwarp();
-      if (lane == 0 && prev_stage >= 0) mbar_arrive(empty0 + 8 * prev_stage);
-      prev_stage = s;
+      // Stage release carries a DATA DEPENDENCY on the slab's fragments.  An mbarrier arrive has no register
+      // operand in common with the ld.shared that filled the fragments, so ptxas may issue it while those loads
+      // are still in flight; the producer then re-arms the stage and the next TMA can overwrite rows a load has
+      // not read yet (round 1: wrong fragments in ~0.3 % of the tiles, masked there by releasing one slab late).
+      // Here the arrive's address is offset by (token & sh.zero): the token ORs the high words of every fragment
+      // register written by the slab's last two k4-steps (same registers as steps 0/1: a register's writes retire
+      // in order, so all of the slab's loads have landed when these are readable), is reduced over the warp
+      // (every lane's loads), and sh.zero is a kernel parameter ptxas cannot fold.  The arrive can therefore not
+      // issue before the slab's last ld.shared has delivered its data, independent of instruction scheduling.
+      uint32_t tok = 0;
+#pragma unroll
+      for (int ni = 0; ni < NI; ni++) tok |= hi32(b[0][ni]) | hi32(b[1][ni]);
+#pragma unroll
+      for (int mi = 0; mi < MI; mi++) tok |= hi32(a[0][mi]) | hi32(a[1][mi]);
+      tok = __reduce_or_sync(0xffffffffu, tok) & sh.zero;
+      if (lane == 0) mbar_arrive(empty0 + 8 * s + tok);
       if (++s == TM_STAGES) { s = 0; ph ^= 1u; }
     }
-    __syncwarp();
-    if (lane == 0 && prev_stage >= 0) mbar_arrive(empty0 + 8 * prev_stage);
-    prev_stage = -1;
     Epi::apply(ep, acc, ti * TM_BM, tj * TM_BN, wm, wn, lane);
   }
   if constexpr (epi_has_finish<Epi>::value) Epi::finish(ep);
@@ -290,12 +300,8 @@ template <class Epi>
 cudaError_t launch_tma_gemm(cudaStream_t s, const CUtensorMap& mapA, const CUtensorMap& mapB, const TmaShape& sh,
                             const typename Epi::Params& ep, int num_sms) {
   auto kern = tma_gemm_kernel<Epi>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  cudaError_t e = configure_kernel_once(reinterpret_cast<const void*>(kern), TM_SMEM_BYTES, false);
+  if (e != cudaSuccess) return e;
   long long ctas = (sh.tiles + 1) / 2;
   if (ctas > num_sms) ctas = num_sms;
   if (ctas < 1) return cudaSuccess;
@@ -303,15 +309,6 @@ cudaError_t launch_tma_gemm(cudaStream_t s, const CUtensorMap& mapA, const CUten
   return cudaGetLastError();
 }
 
-inline int device_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+int device_sm_count();      // SM count of the current device (context.cu)
 
 }  // namespace smnngp

@@ -43,11 +43,16 @@ _ws_cache: dict = {}
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    key = (torch.device(device).index or 0)
+    """Cached scratch buffer per (device, stream): calls enqueued on different streams never share (and so never
+    corrupt) a workspace, and a buffer that has to grow is released to torch's caching allocator, which only hands it
+    out again in the order of the stream it was allocated on (the stream the earlier call was enqueued on)."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
     cur = _ws_cache.get(key)
     if cur is None or cur.numel() < nbytes:
         _ws_cache[key] = None
-        cur = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        cur = torch.empty(int(nbytes), dtype=torch.uint8, device=torch.device("cuda", idx))
         _ws_cache[key] = cur
     return cur
 
@@ -55,6 +60,21 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 def release_workspaces():
     _ws_cache.clear()
     _lib.load().smnngp_host_release()
+
+
+def _on_device_of_first_arg(fn):
+    """Run ``fn`` with the first tensor argument's device current.  The library resolves the device from the stream
+    it is handed, but torch's default stream is the legacy stream (handle 0), which belongs to whatever device is
+    current - so the Python layer pins the device as well."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(x, *a, **k):
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            with torch.cuda.device(x.device):
+                return fn(x, *a, **k)
+        return fn(x, *a, **k)
+    return wrapped
 
 
 def _stream(device):
@@ -83,6 +103,7 @@ def _np_hp(w_std, b_std, last_w_std, eps=1e-6, alpha=2.0, beta=2.0):
 
 
 # ---------------------------------------------------------------------------------------------------------
+@_on_device_of_first_arg
 def gram(x, x2=None, *, spec: StackSpec, hp, shift="none", lower_only=False, out=None):
     """K = kernel_fn(x, x2, get="nngp") (spax/kernels.py:23-27).  Device tensors in, device tensor out."""
     _require_cuda()
@@ -107,6 +128,7 @@ def gram(x, x2=None, *, spec: StackSpec, hp, shift="none", lower_only=False, out
     return out
 
 
+@_on_device_of_first_arg
 def nngp_diag(x, *, spec: StackSpec, hp):
     _require_cuda()
     lib = _lib.load()
@@ -121,6 +143,7 @@ def nngp_diag(x, *, spec: StackSpec, hp):
     return q
 
 
+@_on_device_of_first_arg
 def potrf_(a: torch.Tensor, n_cols=None):
     """In-place lower Cholesky of the leading n_cols x n_cols of the row-major a [M, >=n_cols]; extra rows become
     rows * L^-T.  Returns (sum log L_ii [device scalar], info [device int])."""
@@ -139,6 +162,7 @@ def potrf_(a: torch.Tensor, n_cols=None):
     return logdet, info
 
 
+@_on_device_of_first_arg
 def cov_solve(cov, y, *, scale=1.0, shift=0.0):
     """(sum log L_ii, ||L^-1 y||^2, info) for L = chol(scale * cov + shift I); cov is left untouched."""
     _require_cuda()
@@ -156,6 +180,7 @@ def cov_solve(cov, y, *, scale=1.0, shift=0.0):
     return out[0], out[1], info
 
 
+@_on_device_of_first_arg
 def lml(x, y, *, spec: StackSpec, hp, kind="student_t"):
     """Fused SPR.loss pieces (spax/models.py:93-98).  Device inputs -> (out[4] device tensor, info);
     NumPy inputs -> host entry point, returns (np.ndarray[4], int).
@@ -187,6 +212,7 @@ def lml(x, y, *, spec: StackSpec, hp, kind="student_t"):
     return out, info
 
 
+@_on_device_of_first_arg
 def lml_grad(x, y, *, spec: StackSpec, hp, kind="student_t"):
     """SPR.loss and d loss / d {w_std, b_std, last_w_std, eps, alpha, beta} in one call - the value/gradient pair
     objax.GradValues(model.loss, vars) produces in regression/train.py:62-66 (before the softplus chain rule).
@@ -251,6 +277,10 @@ class LmlGraph:
         _lib.check(rc, "lml (graph)")
 
     def __call__(self, x, y, hp):
+        with torch.cuda.device(self.x.device):
+            return self._call(x, y, hp)
+
+    def _call(self, x, y, hp):
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         self.hp.copy_(hp, non_blocking=True)
@@ -268,6 +298,7 @@ class LmlGraph:
         return self.out, self.info
 
 
+@_on_device_of_first_arg
 def predict(x, y, x_test, *, spec: StackSpec, hp, shift="eps_rel", full_cov=False):
     """NNGPKernel.predict (spax/kernels.py:29-32): returns (mean [T,C], var [T] = diag(cov), info); with
     full_cov=True (device inputs) the second element is the full [T,T] posterior covariance."""
@@ -317,6 +348,7 @@ def predict(x, y, x_test, *, spec: StackSpec, hp, shift="eps_rel", full_cov=Fals
     return mean, var, info
 
 
+@_on_device_of_first_arg
 def test_nll(x, y, x_test, y_test, y_mean, y_std, *, spec: StackSpec, hp, kind="student_t"):
     """Fused SPR.test_nll (spax/models.py:100-120).  Returns (nll, mean [T], var [T], info)."""
     lib = _lib.load()
@@ -359,6 +391,7 @@ def test_nll(x, y, x_test, y_test, y_mean, y_std, *, spec: StackSpec, hp, kind="
     return nll[0], mean, var, info
 
 
+@_on_device_of_first_arg
 def grid_point(x, y, x_test, *, spec: StackSpec, hp):
     """The device work of ONE point (w_std, b_std, eps) of the reference's grid search
     (experiments/regression/find.py:134-160): the predictive with the RELATIVE regulariser (``predict(eps)``,
@@ -393,8 +426,9 @@ class GridSearch:
         self.k0td = torch.empty((self.t, self.ld0), dtype=torch.float64, device=dev)
         self.q_d = torch.empty(self.n, dtype=torch.float64, device=dev)
         self.q_t = torch.empty(self.t, dtype=torch.float64, device=dev)
-        rc = self.lib.smnngp_grid_base_f64(_stream(dev), _p(x), _p(xt), self.n, self.t, d, _p(self.k0dd), self.ld0,
-                                           _p(self.k0td), self.ld0, _p(self.q_d), _p(self.q_t))
+        with torch.cuda.device(dev):
+            rc = self.lib.smnngp_grid_base_f64(_stream(dev), _p(x), _p(xt), self.n, self.t, d, _p(self.k0dd), self.ld0,
+                                               _p(self.k0td), self.ld0, _p(self.q_d), _p(self.q_t))
         _lib.check(rc, "grid_base")
 
     def point(self, hp):
@@ -406,10 +440,11 @@ class GridSearch:
         out = torch.empty(2, dtype=torch.float64, device=dev)
         info = torch.zeros(1, dtype=torch.int32, device=dev)
         ws_bytes = self.lib.smnngp_grid_workspace_bytes(self.n, self.t, nh, arch)
-        ws = _workspace(ws_bytes, dev)
-        rc = self.lib.smnngp_grid_point_f64(_stream(dev), _p(self.k0dd), self.ld0, _p(self.k0td), self.ld0, _p(self.q_d),
-                                            _p(self.q_t), _p(self.y), self.n, self.t, nh, act, arch, _p(hp), _p(ws),
-                                            ws_bytes, _p(mean), _p(var), _p(out), _p(info))
+        with torch.cuda.device(dev):
+            ws = _workspace(ws_bytes, dev)
+            rc = self.lib.smnngp_grid_point_f64(_stream(dev), _p(self.k0dd), self.ld0, _p(self.k0td), self.ld0,
+                                                _p(self.q_d), _p(self.q_t), _p(self.y), self.n, self.t, nh, act, arch,
+                                                _p(hp), _p(ws), ws_bytes, _p(mean), _p(var), _p(out), _p(info))
         _lib.check(rc, "grid_point")
         return mean, var, 2.0 * out[0], out[1], info
 
@@ -420,6 +455,7 @@ def set_panel_width(nb: int):
 
 # ---------------------------------------------------------------------------------------------------------
 # posterior draw stage (classification / ensemble configuration)
+@_on_device_of_first_arg
 def sample_f_iid(mean, var, *, hp, kind="student_t", num_samples, seed=0):
     """Prior.sample_f_iid (spax/priors.py:30-36, :60-68).  mean [T, C] (NNGPKernel.predict layout), var [T] or
     [C, T]  ->  draws [C, T, S]."""
@@ -435,6 +471,7 @@ def sample_f_iid(mean, var, *, hp, kind="student_t", num_samples, seed=0):
     return out
 
 
+@_on_device_of_first_arg
 def draw_metrics(mean, var, label, *, hp, kind="student_t", num_samples, seed=0):
     """Fused draw -> test_log_likelihood / get_correct_count (spax/utils.py:61-74) without materialising the
     [C, T, S] draws.  Returns (nll, correct_count, ll_per_test [T], pred [T])."""

@@ -160,6 +160,20 @@ class CudaBackend:
         return out
 
 
+def _on_own_device(method):
+    """run a driver method with the driver's device current (the C library launches on the current device when it is
+    handed torch's default stream, which is the legacy stream and carries no device of its own)"""
+    import functools
+
+    @functools.wraps(method)
+    def wrapped(self, *a, **k):
+        if self.a.is_cuda:
+            with torch.cuda.device(self.a.device):
+                return method(self, *a, **k)
+        return method(self, *a, **k)
+    return wrapped
+
+
 class PeerUnavailable(RuntimeError):
     """raised on EVERY rank when the peer-memory exchange cannot be set up on some rank"""
 
@@ -513,6 +527,7 @@ class DistributedLML:
             pfull = self.a[ls:ls + (n - c1), c0:c1]
         return ls, m, pfull
 
+    @_on_own_device
     def lml(self, x, y, hp, kind="student_t"):
         """SPR.loss pieces: (out[4] = {log p, loss, sum log L_ii, ||L^-1 y||^2}, info), identical on every rank."""
         be, lay, n, db, P = self.be, self.lay, self.n, self.db, self.world
@@ -642,6 +657,7 @@ class DistributedPredict(DistributedLML):
                 self.carried[:m - k, c0:c1].copy_(self.ploc[p & 1][k:m, :c1 - c0])
         return res
 
+    @_on_own_device
     def predict(self, x, y, x_test, hp):
         """(mean [T, C], var [T] = diag of the posterior covariance, info) - identical on every rank."""
         be, n, c, t, P = self.be, self.n, self.c, self.t, self.world
@@ -672,6 +688,7 @@ class DistributedPredict(DistributedLML):
             dist.all_reduce(var, group=self.group)
         return mean, var, info
 
+    @_on_own_device
     def test_nll(self, x, y, x_test, y_test, y_mean, y_std, hp, kind="student_t"):
         """SPR.test_nll (spax/models.py:100-120): the predictive above (relative regulariser, one right-hand side) +,
         for the Student-t likelihood, the scale d = 2a + y^T ((b/a) K + 1e-6 I)^-1 y (spax/likelihoods.py:60-61) from a

@@ -18,19 +18,28 @@ class NNGPKernel(Module):
         """spax/kernels.py:23-27.  x2 None / same object -> symmetric path (lower tiles + mirror)."""
         return kernel_fn(x, None if (x2 is None or x2 is x) else x2, get="nngp")
 
-    def predict(self, kernel_fn, x, y, x_test, eps=1e-6, full_cov=False):
-        """spax/kernels.py:29-32 (neural_tangents gradient_descent_mse_ensemble, relative diag_reg).
-        Returns (mean [T, C], var [T]); var is diag(cov), the only part the regression path consumes
-        (spax/likelihoods.py:31, :62).  full_cov=True returns the reference's full [T, T] covariance instead."""
+    def predict(self, kernel_fn, x, y, x_test, eps=1e-6, full_cov=True):
+        """spax/kernels.py:29-32 (neural_tangents gradient_descent_mse_ensemble(..., diag_reg=eps)(x_test, "nngp",
+        compute_cov=True), relative regulariser).  Returns ``(mean [T, C], cov [T, T])`` exactly like the reference
+        (its callers do ``cov * y_std ** 2`` and take the diagonal: spax/models.py:116, regression/find.py:146).
+        ``full_cov=False`` is the cheap variant for callers that only need diag(cov): ``(mean, var [T])``.
+        NumPy inputs go through the device path too and come back as NumPy arrays."""
         if not isinstance(kernel_fn, KernelFn):
             raise TypeError("predict needs a kernel_fn built by smnngp nt_kernels")
         import numpy as np
-        if isinstance(x, np.ndarray):
+        host = isinstance(x, np.ndarray)
+        if host and not full_cov:
             mean, var, _ = _dev.predict(x, y, x_test, spec=kernel_fn.spec, hp=kernel_fn.hp_host(eps=eps))
-        else:
-            mean, var, _ = _dev.predict(x, y, x_test, spec=kernel_fn.spec, hp=kernel_fn.hp(x.device, eps=eps),
-                                        full_cov=full_cov)
-        return mean, var
+            return mean, var
+        if host:
+            import torch
+            dev = torch.device("cuda", torch.cuda.current_device())
+            x, y, x_test = (torch.as_tensor(np.ascontiguousarray(v, dtype=np.float64), device=dev) for v in (x, y, x_test))
+        mean, second, _ = _dev.predict(x, y, x_test, spec=kernel_fn.spec, hp=kernel_fn.hp(x.device, eps=eps),
+                                       full_cov=full_cov)
+        if host:
+            return mean.cpu().numpy(), second.cpu().numpy()
+        return mean, second
 
     def get_params(self):
         return (self.w_std.safe_value, self.b_std.safe_value, self.last_w_std.safe_value)

@@ -128,9 +128,6 @@ def _predict_worker(rank, world, port, n, t, c, d, db, q, exchange):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(os.environ.get("SMNNGP_TEST_DIST_PREDICT") != "1",
-                    reason="DistributedPredict is validated under gloo on CPU (tests/test_distributed_cpu.py); its first "
-                           "2-GPU run is pending (round 1 ran out of GPU budget) - opt in with SMNNGP_TEST_DIST_PREDICT=1")
 @pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("n,t,c,db", [(1500, 300, 2, 128), (3000, 700, 1, 256)])
 def test_two_rank_predict_matches_oracle(n, t, c, db, exchange):

@@ -286,7 +286,11 @@ def test_golden_vectors_on_gpu(sm):
 
 
 @pytest.mark.parametrize("m,n,k,lower", [(2745, 2744, 256, 1), (2816, 2752, 256, 0), (4096, 4160, 16, 0),
-                                         (4096, 4096, 128, 0), (8192, 8256, 512, 1), (1000, 130, 48, 0)])
+                                         (4096, 4096, 128, 0), (8192, 8256, 512, 1), (1000, 130, 48, 0),
+                                         # short K, many tiles per CTA: the release of a tile's LAST slab is followed by
+                                         # the epilogue, not by another slab (the window the delayed release left open)
+                                         (12288, 12288, 16, 0), (12288, 12288, 32, 1), (16384, 8192, 48, 0),
+                                         (9000, 9100, 128, 1)])
 def test_update_kernel_many_tiles_per_cta(sm, m, n, k, lower):
     """C -= A B^T on the TMA-fed persistent kernel when every math group walks through several tiles (regression
     test for the stage-release race: a stage released while ld.shared was in flight got overwritten by TMA)."""
@@ -398,3 +402,94 @@ def test_grid_search_with_cached_base(sm, n, t, d, act, arch, L):
         m2, v2, ld2, q2, _ = sm.device.grid_point(xd, yd, xtd, spec=spec, hp=hpd)      # from scratch
         assert np.abs((mean - m2).cpu().numpy()).max() <= 1e-11 * np.abs(mean_ref).max()
         assert abs(logdet.item() - ld2.item()) <= 1e-11 * abs(logdet_ref)
+
+
+# ---- BASELINE configs at (or near) their named sizes --------------------------------------------------------------
+def test_c2_uci_shape_lml_and_test_nll(sm):
+    """BASELINE config 2: N = 10 000, D = 8, T = 1000, 3-layer ReLU, Student-t - SPR.loss and SPR.test_nll against the
+    oracle (spax/models.py:93-120).  The oracle needs ~15 s of host time at this size."""
+    import torch
+    n, d, t = 10000, 8, 1000
+    x, y, xt, yt, ym, ys = regression_data(n, d, t=t)
+    hp, hpd = _hp(sm)
+    spec = sm.StackSpec(3, "relu", "mlp")
+    kw = _kw(hp, 3, "relu", "mlp")
+    xd, yd, xtd, ytd = (torch.from_numpy(v).cuda() for v in (x, y, xt, yt))
+    out, info = sm.device.lml(xd, yd, spec=spec, hp=hpd)
+    ref = orc.spr_loss(x, y, eps=hp["eps"], kind="student_t", a=hp["alpha"], b=hp["beta"], fast=True, **kw)
+    assert int(info.item()) == 0
+    assert abs(out[1].item() - ref) <= LML_TOL * abs(ref), (out[1].item(), ref)
+    nll, mean, var, info = sm.device.test_nll(xd, yd, xtd, ytd, ym, ys, spec=spec, hp=hpd)
+    ref_nll = orc.spr_test_nll(x, y, xt, yt, ym, ys, eps=hp["eps"], kind="student_t", a=hp["alpha"], b=hp["beta"], **kw)
+    assert int(info.item()) == 0
+    assert abs(float(nll.item()) - ref_nll) <= LML_TOL * abs(ref_nll), (float(nll.item()), ref_nll)
+
+
+def test_c4_cifar_shape_predict(sm):
+    """BASELINE config 4 shape (D = 3072, C = 10 one-hot-centred targets) at N = 8192, T = 2048: NNGPKernel.predict
+    (spax/kernels.py:29-32) - mean and diag(cov) against the oracle (not against another GPU library)."""
+    import torch
+    n, d, t, c = 8192, 3072, 2048, 10
+    rng = np.random.default_rng(10)
+    x = rng.standard_normal((n + t, d))
+    lab = rng.integers(0, c, n)
+    Y = np.eye(c)[lab] - 1.0 / c
+    x, xt = np.ascontiguousarray(x[:n]), np.ascontiguousarray(x[n:])
+    hp, hpd = _hp(sm, eps=1e-4)
+    spec = sm.StackSpec(3, "relu", "mlp")
+    kw = _kw(hp, 3, "relu", "mlp")
+    mean_ref, cov_ref = orc.nt_predict(x, Y, xt, hp["eps"], kernel_kwargs=kw)
+    vref, ktt = np.diag(cov_ref), orc.nngp_diag(xt, **kw)
+    mean, var, info = sm.device.predict(torch.from_numpy(x).cuda(), torch.from_numpy(Y).cuda(),
+                                        torch.from_numpy(xt).cuda(), spec=spec, hp=hpd)
+    assert int(info.item()) == 0
+    mean, var = mean.cpu().numpy(), var.cpu().numpy()
+    assert np.abs(mean - mean_ref).max() <= LML_TOL * np.abs(mean_ref).max()
+    assert np.all(np.abs(var - vref) <= LML_TOL * np.abs(vref) + 1e-13 * ktt)
+
+
+def test_c3_full_size_matches_oracle_golden(sm):
+    """BASELINE config 3 at FULL size (N = 60 000, D = 784): the fused LML against the oracle value recorded once by
+    tests/golden/make_c3_golden.py on the GPU box's host cores (tests/golden/c3_full.json), tolerance 1e-8."""
+    import json
+    import os
+    import torch
+    path = os.path.join(os.path.dirname(__file__), "golden", "c3_full.json")
+    with open(path) as f:
+        g = json.load(f)
+    if g.get("oracle_loss") is None:
+        pytest.skip("tests/golden/c3_full.json holds no oracle value yet")
+    if torch.cuda.get_device_properties(0).total_memory < 40e9:
+        pytest.skip("needs 30 GB of device memory")
+    x, y, *_ = pixel_data(g["n"], g["d"], seed=g["seed"])
+    hp, hpd = _hp(sm, **g["hp"])
+    sm.device.release_workspaces()
+    torch.cuda.empty_cache()
+    out, info = sm.device.lml(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), spec=sm.StackSpec(3, "relu", "mlp"),
+                              hp=hpd)
+    got = float(out[1].item())
+    sm.device.release_workspaces()
+    torch.cuda.empty_cache()
+    assert int(info.item()) == 0
+    assert abs(got - g["oracle_loss"]) <= LML_TOL * abs(g["oracle_loss"]), (got, g["oracle_loss"])
+    assert abs(float(out[2].item()) - (g["oracle_sum_log_diag"] - 0.5 * g["n"] * np.log(g["hp"]["beta"] / g["hp"]["alpha"]))) \
+        <= 1e-9 * abs(g["oracle_sum_log_diag"]) + 1e-6
+
+
+def test_second_device_in_one_process(sm):
+    """single-process multi-device callers (JAX): a call on a tensor of a device that is NOT current must launch there
+    (device resolved from the stream / tensor, per-device context: smem attributes, side stream, arena)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    x, y, *_ = regression_data(2500, 8)
+    hp, _ = _hp(sm)
+    ref = orc.spr_loss(x, y, eps=hp["eps"], kind="student_t", a=hp["alpha"], b=hp["beta"], **_kw(hp, 3, "relu", "mlp"))
+    assert torch.cuda.current_device() == 0
+    for dev in ("cuda:1", "cuda:0", "cuda:1"):
+        hpd = sm.make_hp(device=dev, **hp)
+        out, info = sm.device.lml(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev),
+                                  spec=sm.StackSpec(3, "relu", "mlp"), hp=hpd)
+        assert out.device == torch.device(dev) and int(info.item()) == 0
+        assert abs(out[1].item() - ref) <= LML_TOL * abs(ref)
+    assert torch.cuda.current_device() == 0

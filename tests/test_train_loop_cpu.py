@@ -61,17 +61,41 @@ def test_training_loop_decreases_the_loss_and_names_match():
     assert any("nll:" in s for s in lines) and any("TEST:" in s for s in lines)
 
 
-def test_adam_matches_reference_update_rule_and_skips_nan():
-    import smnngp_b200 as sm
+def _objax_adam_step(p, m, v, g, lr, step, b1=0.9, b2=0.999, eps=1e-8):
+    """objax.optimizer.Adam.__call__ written out by hand: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t),
+    m = b1 m + (1 - b1) g, v = b2 v + (1 - b2) g^2, p -= lr_t * m * rsqrt(v + eps)   (eps INSIDE the square root)."""
+    import math
+    lr_t = lr * math.sqrt(1.0 - b2 ** step) / (1.0 - b1 ** step)
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    return p - lr_t * m / math.sqrt(v + eps), m, v
+
+
+def test_adam_matches_objax_update_rule():
+    import math
     from smnngp_b200.spax import Adam, ConstraintTrainVar, positive
+    # (a) ordinary gradient, (b) the tiny gradient of b_std at the reference defaults (|g| ~ 1e-8): with eps inside the
+    # square root the step is ~lr * 1e-4, with sqrt(v) + eps it would be ~lr - orders of magnitude apart
+    for grads in ([2.0, -1.5, 0.7], [5e-8, 3e-8, -4e-8]):
+        v = ConstraintTrainVar(1.5, constraint=positive())
+        opt = Adam({"v": v})
+        p, m, vv = float(v.value), 0.0, 0.0
+        for step, g in enumerate(grads, 1):
+            opt(0.1, {"v": g})
+            p, m, vv = _objax_adam_step(p, m, vv, g, 0.1, step)
+            assert abs(float(v.value) - p) <= 1e-15 * max(1.0, abs(p)), (step, float(v.value), p)
     v = ConstraintTrainVar(1.5, constraint=positive())
     raw0 = float(v.value)
-    opt = Adam({"v": v})
-    opt(0.1, {"v": 2.0})
-    # first Adam step moves by lr * sign(g) (bias-corrected m / sqrt(v) = 1)
-    assert abs(float(v.value) - (raw0 - 0.1)) <= 1e-6
+    Adam({"v": v})(0.1, {"v": 5e-8})
+    assert abs(float(v.value) - raw0) < 0.1 * 1e-3            # effectively frozen, as in the reference
+    # NaN gradients propagate like in objax; skipping them is an explicit opt-in
+    v = ConstraintTrainVar(1.5, constraint=positive())
+    Adam({"v": v})(0.1, {"v": float("nan")})
+    assert math.isnan(float(v.value))
+    v = ConstraintTrainVar(1.5, constraint=positive())
+    opt = Adam({"v": v}, skip_nan=True)
     opt(0.1, {"v": float("nan")})
-    assert abs(float(v.value) - (raw0 - 0.1)) <= 1e-6 and opt.step == 1
+    assert float(v.value) == raw0 and opt.step == 0
     g = float(positive().grad(v.value))
     h = 1e-6
     assert abs(g - (float(positive()(v.value + h)) - float(positive()(v.value - h))) / (2 * h)) <= 1e-8
