@@ -224,6 +224,46 @@ int smnngp_stage_trsm_scatter_f64(void* stream, const double* R, int64_t ldr, in
                                   int64_t db, int64_t local_row0, int64_t c1, int64_t n, int64_t ld_peer,
                                   void* const* flag_ptrs, int64_t flag_index, uint64_t seq, unsigned int* counter);
 
+/* W = inv(L) of a factored panel diagonal block (w <= 512) assembled from L and the inverses of its 128 x 128
+ * diagonal blocks (what smnngp_stage_factor_diag_f64 leaves behind), stored into the W buffer of every rank; when
+ * flag_ptrs / counter are given the last CTA sets flag word `flag_index` on every rank to seq */
+int smnngp_stage_assemble_inverse_f64(void* stream, const double* L, int64_t ldl, int64_t w, const double* linv_blocks,
+                                      void* const* dst_ptrs, int P, int64_t ldw, void* const* flag_ptrs,
+                                      int64_t flag_index, uint64_t seq, unsigned int* counter);
+
+/* ---- multi-GPU in ONE call per rank (csrc/multigpu.cu; SURVEY.md section 8b "multi-GPU variants", 8e) ------------
+ * Replaces, for the sharded case, the same reference lines as smnngp_lml_f64 (spax/models.py:93-98 under objax.Jit,
+ * experiments/regression/train.py:61-67).  One handle per rank owns everything the distributed factorisation needs
+ * (row shard of K, NVLink-visible panel / W / flag / reduce buffers, side stream, watchdog); the library needs no
+ * communicator: the caller moves the 64-byte IPC handles between the processes once (any transport), or connects
+ * several devices of one process by pointer.
+ *   smnngp_mg_create         on the rank's device (current device); block = distribution block = outer panel width
+ *                            (multiple of 128, <= 512)
+ *   smnngp_mg_ipc_handle     64-byte CUDA IPC handle of the rank's peer-visible region
+ *   smnngp_mg_connect_ipc    handles = world x 64 bytes, rank-major (one process per GPU)
+ *   smnngp_mg_connect_ptrs   regions[r] = smnngp_mg_region() of rank r (same process, peer access enabled inside)
+ *   smnngp_mg_connect_emulated  timing dry-run of one rank on one device (all peers alias the local region)
+ *   smnngp_lml_mg_f64        enqueue-only on `stream` (same device as the handle); every rank passes the same X, y, hp
+ *                            (device pointers on ITS device); out_dev[4] as smnngp_lml_f64, identical on every rank;
+ *                            shift = SMNNGP_SHIFT_* added to the Gram diagonal (SMNNGP_SHIFT_EPS_ABS for SPR.loss)
+ *   a peer that dies cannot hang the GPU: a host watchdog releases the stream waits after the time-out (default 20 s)
+ *   and poisons info (all results NaN); the handle is unusable afterwards */
+typedef struct smnngp_mg smnngp_mg;
+int smnngp_mg_create(smnngp_mg** out, int rank, int world, int64_t n, int64_t block);
+int smnngp_mg_destroy(smnngp_mg* g);
+int smnngp_mg_ipc_handle(smnngp_mg* g, unsigned char* handle_out64);
+void* smnngp_mg_region(smnngp_mg* g);
+int smnngp_mg_connect_ipc(smnngp_mg* g, const unsigned char* handles);
+int smnngp_mg_connect_ptrs(smnngp_mg* g, void* const* regions, const int* peer_devices);
+int smnngp_mg_connect_emulated(smnngp_mg* g);
+void smnngp_mg_set_timeout(smnngp_mg* g, double seconds);
+void smnngp_mg_set_sm_reserve(smnngp_mg* g, int sms);         /* < 0: automatic (default) */
+void smnngp_mg_timeline(smnngp_mg* g, int enable);            /* profiling: CUDA events at the stage boundaries */
+int smnngp_mg_timeline_read(smnngp_mg* g, int cap, int* panel_out, int* label_out, double* ms_out);
+const char* smnngp_mg_last_error(void);
+int smnngp_lml_mg_f64(smnngp_mg* g, void* stream, const double* X, const double* y, int64_t D, int n_hidden, int act,
+                      int arch, const double* hp_dev, int kind, int shift, double* out_dev, int* info_dev);
+
 /* ---- peer memory (multi-GPU, one process per GPU): cudaMalloc'ed buffers exported / imported as 64-byte CUDA IPC
  * handles so that every rank can store into every other rank's panel buffer over NVLink (no reference
  * counterpart: the reference is single-device). */
@@ -256,6 +296,14 @@ void smnngp_set_tile_variant(int v);
  * high-priority side stream while the bulk of the trailing update runs (fork / join with events: still
  * enqueue-only and graph-capturable); 0 = single stream */
 void smnngp_set_lookahead(int on);
+/* 1 (default): per outer panel the rows below the diagonal block are solved by ONE launch (full inverse of the block,
+ * out of place); 0: 128-block substitution in place (round-1 path).  Applies to the current device. */
+void smnngp_set_fused_panel(int on);
+/* tuning knob: L2-aware tile walk of the Gram kernel - tiles are visited in square super-tiles of `sr` x 2 sr tiles
+ * (128 sr elements a side) so that the operand rows of the tiles in flight stay L2 resident; 0 = row-major walk.
+ * Used when the column operand (M x D doubles) is at least min_operand_bytes (default 40 MB; < 0 restores it).
+ * Default sr = 8.  Applies to the current device. */
+void smnngp_set_gram_super_rows(int sr, int64_t min_operand_bytes);
 /* tuning knob: SMs the bulk trailing update leaves free for the look-ahead chain (the persistent update kernel
  * would otherwise hold every SM until it ends): trailing matrix narrower than 24000 columns / wider.  Default 8, 0
  * (measured at C3: reserving even 1 SM costs more than the exposed diagonal-block chain, 2234 vs 2224 ms) */

@@ -30,7 +30,10 @@ NIT = int(os.environ.get("PROF_ITERS", "4"))
 for it in range(NIT):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if it == NIT - 1 and os.environ.get("PROF_TIMELINE", "1") != "0":
+    want_tl = it == NIT - 1 and os.environ.get("PROF_TIMELINE", "1") != "0"
+    if want_tl and job.mg is not None:
+        job.enable_timeline()                                # C driver (smnngp_lml_mg_f64): events recorded inside
+    elif want_tl:
         job.timeline = []
         if os.environ.get("PROF_TIMELINE") == "side":      # no timing events between the main-stream kernels
             job._tl_filter = ("main_start", "diag", "bcast", "trsm", "gather", "reorder")
@@ -39,14 +42,20 @@ for it in range(NIT):
     e1.record()
     torch.cuda.synchronize()
     print(f"{'real' if REAL else 'emulated'} {job.exchange} P={P} rank={rank} N={n}: {e0.elapsed_time(e1):.2f} ms", flush=True)
-if job.timeline is None:
+c_marks = job.timeline_read() if job.mg is not None else None
+if job.timeline is None and not c_marks:
     if REAL:
         dist.barrier()
         dist.destroy_process_group()
     sys.exit(0)
 tl = {}
-for p, label, ev in job.timeline:
-    tl.setdefault(p, {})[label] = e0.elapsed_time(ev)
+if c_marks:
+    # times are relative to the first mark = the start of the evaluation (before the Gram stage)
+    for p, label, ms in c_marks:
+        tl.setdefault(p, {})[label] = ms
+else:
+    for p, label, ev in job.timeline:
+        tl.setdefault(p, {})[label] = e0.elapsed_time(ev)
 npan = max(tl) + 1
 tot_a = tot_b = tot_wait = 0.0
 prev_end = tl[0].get("main_start", 0.0)

@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsmnngp.so")
 SOURCES = ["gram.cu", "chol.cu", "reduce.cu", "api.cu", "stages.cu", "draws.cu", "grad.cu", "peer.cu", "exchange.cu",
-           "context.cu"]
+           "context.cu", "trtri.cu", "multigpu.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets"]
 
@@ -26,7 +26,7 @@ EXPORTS = [
     "smnngp_lml_workspace_bytes", "smnngp_lml_f64", "smnngp_lml_grad_workspace_bytes", "smnngp_lml_grad_f64",
     "smnngp_lml_grad_host_f64", "smnngp_predict_workspace_bytes", "smnngp_predict_f64", "smnngp_predict_cov_f64",
     "smnngp_test_nll_f64", "smnngp_lml_host_f64", "smnngp_predict_host_f64", "smnngp_test_nll_host_f64",
-    "smnngp_host_release", "smnngp_set_panel_width", "smnngp_set_tile_variant", "smnngp_debug_occupancy", "smnngp_set_lookahead", "smnngp_set_lookahead_reserve", "smnngp_debug_potf2_clocks",
+    "smnngp_host_release", "smnngp_set_panel_width", "smnngp_set_tile_variant", "smnngp_debug_occupancy", "smnngp_set_lookahead", "smnngp_set_fused_panel", "smnngp_set_gram_super_rows", "smnngp_set_lookahead_reserve", "smnngp_debug_potf2_clocks",
     "smnngp_sample_f_iid_f64", "smnngp_draw_metrics_f64",
     "smnngp_grid_base_f64", "smnngp_grid_workspace_bytes", "smnngp_grid_point_f64",
     "smnngp_stage_qtable_f64", "smnngp_stage_gram_f64", "smnngp_stage_factor_diag_f64", "smnngp_stage_trsm_f64",
@@ -37,6 +37,10 @@ EXPORTS = [
     "smnngp_stage_push_panel_f64",
     "smnngp_peer_alloc", "smnngp_peer_open", "smnngp_peer_close", "smnngp_peer_free",
     "smnngp_instr_reset", "smnngp_instr_launches", "smnngp_instr_updates", "smnngp_dmma_peak_tflops",
+    "smnngp_stage_assemble_inverse_f64",
+    "smnngp_mg_create", "smnngp_mg_destroy", "smnngp_mg_ipc_handle", "smnngp_mg_region", "smnngp_mg_connect_ipc",
+    "smnngp_mg_connect_ptrs", "smnngp_mg_connect_emulated", "smnngp_mg_set_timeout", "smnngp_mg_set_sm_reserve",
+    "smnngp_mg_timeline", "smnngp_mg_timeline_read", "smnngp_mg_last_error", "smnngp_lml_mg_f64",
 ]
 
 
@@ -150,6 +154,10 @@ def _declare(lib):
     lib.smnngp_set_lookahead_reserve.argtypes = [_i, _i]
     lib.smnngp_set_lookahead.restype = None
     lib.smnngp_set_lookahead.argtypes = [_i]
+    lib.smnngp_set_fused_panel.restype = None
+    lib.smnngp_set_fused_panel.argtypes = [_i]
+    lib.smnngp_set_gram_super_rows.restype = None
+    lib.smnngp_set_gram_super_rows.argtypes = [_i, _i64]
     lib.smnngp_grid_base_f64.argtypes = [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _vp]
     lib.smnngp_grid_workspace_bytes.restype = _sz
     lib.smnngp_grid_workspace_bytes.argtypes = [_i64, _i64, _i, _i]
@@ -184,6 +192,24 @@ def _declare(lib):
     lib.smnngp_peer_open.argtypes = [_vp, _vp]
     lib.smnngp_peer_close.argtypes = [_vp]
     lib.smnngp_peer_free.argtypes = [_vp]
+    lib.smnngp_stage_assemble_inverse_f64.argtypes = [_vp, _vp, _i64, _i64, _vp, _vp, _i, _i64, _vp, _i64, _u64, _vp]
+    lib.smnngp_mg_create.argtypes = [_vp, _i, _i, _i64, _i64]
+    lib.smnngp_mg_destroy.argtypes = [_vp]
+    lib.smnngp_mg_ipc_handle.argtypes = [_vp, _vp]
+    lib.smnngp_mg_region.restype = _vp
+    lib.smnngp_mg_region.argtypes = [_vp]
+    lib.smnngp_mg_connect_ipc.argtypes = [_vp, _vp]
+    lib.smnngp_mg_connect_ptrs.argtypes = [_vp, _vp, _vp]
+    lib.smnngp_mg_connect_emulated.argtypes = [_vp]
+    lib.smnngp_mg_set_timeout.restype = None
+    lib.smnngp_mg_set_timeout.argtypes = [_vp, _d]
+    lib.smnngp_mg_set_sm_reserve.restype = None
+    lib.smnngp_mg_set_sm_reserve.argtypes = [_vp, _i]
+    lib.smnngp_mg_timeline.restype = None
+    lib.smnngp_mg_timeline.argtypes = [_vp, _i]
+    lib.smnngp_mg_timeline_read.argtypes = [_vp, _i, _vp, _vp, _vp]
+    lib.smnngp_mg_last_error.restype = C.c_char_p
+    lib.smnngp_lml_mg_f64.argtypes = [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _i, _vp, _vp]
     lib.smnngp_instr_reset.restype = None
     lib.smnngp_instr_reset.argtypes = [_i]
     lib.smnngp_instr_launches.restype = C.c_longlong

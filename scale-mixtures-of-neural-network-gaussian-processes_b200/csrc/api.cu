@@ -79,7 +79,7 @@ size_t carve_gram(Carver& c, GramWs& w, long long N, long long M, int n_act, boo
 }
 
 struct SolveWs {
-  double *scal, *scal2, *tab, *q, *tab_t, *q_t, *linv, *A, *mean, *var;
+  double *scal, *scal2, *tab, *q, *tab_t, *q_t, *linv, *A, *mean, *var, *fws;
   long long lda, rows;
 };
 // A holds N train rows + T cross-Gram rows + C right-hand-side rows
@@ -97,6 +97,7 @@ size_t carve_solve(Carver& c, SolveWs& w, long long N, long long T, long long C,
   w.lda = round_up(N, 16);
   w.rows = N + T + C;
   w.A = c.take<double>((size_t)w.rows * w.lda);
+  w.fws = c.take<double>(fused_ws_doubles(w.rows));          // W + panel buffer of the single-launch panel solve
   return c.total();
 }
 
@@ -145,6 +146,13 @@ void smnngp_set_panel_width(int nb) { dctx().panel_width = nb > 0 ? (nb + PB - 1
 void smnngp_set_tile_variant(int v) { tile_variant() = (v >= 0 && v <= 2) ? v : 0; }
 int smnngp_debug_occupancy(int variant) { return debug_gemm_occupancy(variant); }
 void smnngp_set_lookahead(int on) { lookahead_mode() = on ? 1 : 0; }
+// 1 (default): single-launch panel solve with the diagonal block's full inverse; 0: 128-block substitution in place
+void smnngp_set_fused_panel(int on) { dctx().fused_panel = on ? 1 : 0; }
+// super-tile height (128-row tiles) of the Gram kernel's L2-aware tile walk; 0 = row-major walk (round-1 behaviour)
+void smnngp_set_gram_super_rows(int sr, int64_t min_operand_bytes) {
+  dctx().gram_super = sr < 0 ? 0 : (sr > 64 ? 64 : sr);
+  dctx().gram_super_min_bytes = min_operand_bytes < 0 ? 40000000 : min_operand_bytes;
+}
 void smnngp_set_lookahead_reserve(int small_trailing, int large_trailing) {
   lookahead_reserve()[0] = small_trailing < 0 ? 0 : small_trailing;
   lookahead_reserve()[1] = large_trailing < 0 ? 0 : large_trailing;
@@ -224,10 +232,12 @@ int smnngp_nngp_diag_f64(void* stream, const double* X, int64_t N, int64_t D, in
 
 // ---------------------------------------------------------------------------------------------------------
 size_t smnngp_potrf_workspace_bytes(int64_t N) {
-  (void)N;
+  // sized for the square case; a trapezoid with M > N rows falls back to the in-place panel solve when the panel
+  // buffer does not fit (see smnngp_potrf_trapezoid_f64)
   Carver c(nullptr);
   c.take<double>(SC_COUNT);
   c.take<double>(LINV_BLOCKS * PB * PB);
+  c.take<double>(fused_ws_doubles(N > 0 ? N : 0));
   return c.total();
 }
 
@@ -242,10 +252,12 @@ int smnngp_potrf_trapezoid_f64(void* stream, double* A, int64_t M, int64_t N, in
   double* linv = c.take<double>(LINV_BLOCKS * PB * PB);
   if (c.total() > workspace_bytes || !workspace)
     return fail(SMNNGP_EWORKSPACE, "smnngp_potrf_trapezoid_f64: workspace too small");
+  double* fws = c.take<double>(fused_ws_doubles(M));           // optional: enables the single-launch panel solve
+  if (c.total() > workspace_bytes) fws = nullptr;
   CU(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
   CU(cudaMemsetAsync(scal, 0, SC_COUNT * sizeof(double), s));
   if (N == 0) return SMNNGP_OK;
-  CU(potrf_trapezoid(s, A, ld, M, N, pick_nb(N), linv, scal + SC_LOGDET, info_dev));
+  CU(potrf_trapezoid(s, A, ld, M, N, pick_nb(N), linv, scal + SC_LOGDET, info_dev, 0, -1, fws, true));
   if (logdet_dev) CU(cudaMemcpyAsync(logdet_dev, scal + SC_LOGDET, sizeof(double), cudaMemcpyDeviceToDevice, s));
   return SMNNGP_OK;
 }
@@ -266,6 +278,7 @@ size_t smnngp_cov_solve_workspace_bytes(int64_t N) {
   c.take<double>(SC_COUNT);
   c.take<double>(LINV_BLOCKS * PB * PB);
   c.take<double>((size_t)(N + 1) * round_up(N, 16));
+  c.take<double>(fused_ws_doubles(N + 1));
   return c.total();
 }
 
@@ -290,6 +303,7 @@ int smnngp_cov_solve_f64(void* stream, const double* cov, int64_t N, int64_t ld,
   double* linv = c.take<double>(LINV_BLOCKS * PB * PB);
   const long long lda = round_up(N, 16);
   double* A = c.take<double>((size_t)(N + 1) * lda);
+  double* fws = c.take<double>(fused_ws_doubles(N + 1));
   if (c.total() > workspace_bytes || !workspace)
     return fail(SMNNGP_EWORKSPACE, "smnngp_cov_solve_f64: workspace too small");
   CU(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
@@ -299,7 +313,7 @@ int smnngp_cov_solve_f64(void* stream, const double* cov, int64_t N, int64_t ld,
   instr().launches++;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(A + N * lda, y, N * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  CU(potrf_trapezoid(s, A, lda, N + 1, N, pick_nb(N), linv, scal + SC_LOGDET, info_dev));
+  CU(potrf_trapezoid(s, A, lda, N + 1, N, pick_nb(N), linv, scal + SC_LOGDET, info_dev, 0, -1, fws, false));
   CU(launch_sumsq(s, A + N * lda, N, scal + SC_QUAD));
   CU(cudaMemcpyAsync(out_dev, scal + SC_LOGDET, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
   CU(launch_fill_nan_if_bad(s, info_dev, out_dev, 2));
@@ -334,7 +348,7 @@ int smnngp_lml_f64(void* stream, const double* X, const double* y, int64_t N, in
   CU(enqueue_sym_gram(s, X, N, D, n_hidden, act, arch, hp_dev, w.tab, w.scal, SHIFT_EPS_ABS, 0, w.A, w.lda));
   // y^T appended as row N: the factorisation turns it into (L^-1 y)^T (spax/utils.py:180)
   CU(cudaMemcpyAsync(w.A + N * w.lda, y, N * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  CU(potrf_trapezoid(s, w.A, w.lda, N + 1, N, pick_nb(N), w.linv, w.scal + SC_LOGDET, info_dev));
+  CU(potrf_trapezoid(s, w.A, w.lda, N + 1, N, pick_nb(N), w.linv, w.scal + SC_LOGDET, info_dev, 0, -1, w.fws, false));
   CU(launch_sumsq(s, w.A + N * w.lda, N, w.scal + SC_QUAD));
   CU(launch_lml_finalize(s, w.scal, hp_dev, kind, N, info_dev, out_dev));
   return SMNNGP_OK;
@@ -344,7 +358,7 @@ int smnngp_lml_f64(void* stream, const double* X, const double* y, int64_t N, in
 // loss and its gradient w.r.t. the six scalars
 namespace {
 struct GradWs {
-  double *scal, *tab, *q, *tab3, *linv, *alpha, *partial, *A;
+  double *scal, *tab, *q, *tab3, *linv, *alpha, *partial, *A, *fws;
   long long lda, slots;
 };
 size_t carve_grad(Carver& c, GradWs& w, long long N, int n_act) {
@@ -359,6 +373,7 @@ size_t carve_grad(Carver& c, GradWs& w, long long N, int n_act) {
   w.partial = c.take<double>((size_t)w.slots * 4);
   w.lda = round_up(N, 16);
   w.A = c.take<double>((size_t)(2 * N + 1) * w.lda);   // K -> L -> A^-1 | y^T -> z^T | I -> U = L^-T
+  w.fws = c.take<double>(fused_ws_doubles(2 * N + 1));
   return c.total();
 }
 }  // namespace
@@ -394,7 +409,7 @@ int smnngp_lml_grad_f64(void* stream, const double* X, const double* y, int64_t 
   CU(cudaMemcpyAsync(zrow, y, N * sizeof(double), cudaMemcpyDeviceToDevice, s));
   CU(launch_set_identity(s, U, w.lda, N));
   // forward value exactly as smnngp_lml_f64; the identity rows come out as U = L^-T
-  CU(potrf_trapezoid(s, w.A, w.lda, 2 * N + 1, N, pick_nb(N), w.linv, w.scal + SC_LOGDET, info_dev, 0, N + 1));
+  CU(potrf_trapezoid(s, w.A, w.lda, 2 * N + 1, N, pick_nb(N), w.linv, w.scal + SC_LOGDET, info_dev, 0, N + 1, w.fws, false));
   CU(launch_sumsq(s, zrow, N, w.scal + SC_QUAD));
   CU(launch_lml_finalize(s, w.scal, hp_dev, kind, N, info_dev, out_dev));
   // a = A^-1 y = U z;  A^-1 = U U^T over the (now free) lower triangle of the factor
@@ -438,7 +453,7 @@ static int predict_enqueue(cudaStream_t s, const double* X, const double* Y, con
     instr().launches++;
     CU(cudaGetLastError());
   }
-  CU(potrf_trapezoid(s, w.A, w.lda, N + T + C, N, pick_nb(N), w.linv, w.scal + SC_LOGDET, info_dev));
+  CU(potrf_trapezoid(s, w.A, w.lda, N + T + C, N, pick_nb(N), w.linv, w.scal + SC_LOGDET, info_dev, 0, -1, w.fws, false));
   CU(launch_predict_finalize(s, w.A + N * w.lda, w.lda, w.A + (N + T) * w.lda, w.lda, w.q_t, (int)T, (int)C, N,
                              info_dev, mean_out, var_out));
   if (cov_out) {
@@ -521,7 +536,7 @@ int smnngp_test_nll_f64(void* stream, const double* X, const double* y, const do
     CU(enqueue_sym_gram(s, X, N, D, n_hidden, act, arch, hp_dev, w.tab, w.scal, SHIFT_LIK, 0, w.A, w.lda));
     CU(cudaMemcpyAsync(w.A + N * w.lda, y, N * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CU(cudaMemsetAsync(w.scal2, 0, SC_COUNT * sizeof(double), s));
-    CU(potrf_trapezoid(s, w.A, w.lda, N + 1, N, pick_nb(N), w.linv, w.scal2 + SC_LOGDET, info_dev));
+    CU(potrf_trapezoid(s, w.A, w.lda, N + 1, N, pick_nb(N), w.linv, w.scal2 + SC_LOGDET, info_dev, 0, -1, w.fws, false));
     CU(launch_sumsq(s, w.A + N * w.lda, N, w.scal2 + SC_QUAD));
   }
   CU(launch_test_nll_finalize(s, mean, var, yt, (int)T, N, y_mean, y_std, hp_dev, kind, w.scal2 + SC_QUAD,
@@ -586,7 +601,7 @@ int smnngp_grid_point_f64(void* stream, const double* K0dd, int64_t ld0, const d
     CU(launch_gram_from_base(s, x, K0td, ld0t));
   }
   CU(cudaMemcpyAsync(w.A + (N + T) * w.lda, y, N * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  CU(potrf_trapezoid(s, w.A, w.lda, N + T + 1, N, pick_nb(N), w.linv, w.scal + SC_LOGDET, info_dev));
+  CU(potrf_trapezoid(s, w.A, w.lda, N + T + 1, N, pick_nb(N), w.linv, w.scal + SC_LOGDET, info_dev, 0, -1, w.fws, false));
   CU(launch_predict_finalize(s, w.A + N * w.lda, w.lda, w.A + (N + T) * w.lda, w.lda, w.q_t, (int)T, 1, N, info_dev,
                              mean_out, var_out));
   // (2) log det(K + eps I) and y^T (K + eps I)^-1 y with the ABSOLUTE jitter (find.py:149-156)
@@ -594,7 +609,7 @@ int smnngp_grid_point_f64(void* stream, const double* K0dd, int64_t ld0, const d
   CU(launch_gram_from_base(s, g, K0dd, ld0));
   CU(cudaMemcpyAsync(w.A + N * w.lda, y, N * sizeof(double), cudaMemcpyDeviceToDevice, s));
   CU(cudaMemsetAsync(w.scal2, 0, SC_COUNT * sizeof(double), s));
-  CU(potrf_trapezoid(s, w.A, w.lda, N + 1, N, pick_nb(N), w.linv, w.scal2 + SC_LOGDET, info_dev));
+  CU(potrf_trapezoid(s, w.A, w.lda, N + 1, N, pick_nb(N), w.linv, w.scal2 + SC_LOGDET, info_dev, 0, -1, w.fws, false));
   CU(launch_sumsq(s, w.A + N * w.lda, N, w.scal2 + SC_QUAD));
   CU(cudaMemcpyAsync(out_dev, w.scal2 + SC_LOGDET, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
   CU(launch_fill_nan_if_bad(s, info_dev, out_dev, 2));

@@ -136,7 +136,7 @@ cudaError_t launch_gemm_tma(cudaStream_t s, const GemmParams& p) {
     return cudaErrorInvalidValue;
   const int tri = p.lower && p.cyc_db == 0;
   TmaShape sh{p.M, p.N, p.K, tri, count_tiles<TileTma>(p.M, p.N, tri), p.lower ? p.cyc_db : 0, p.cyc_p, p.base_shift,
-              p.k_from_row};
+              p.k_from_row, p.k_upto_col};
   if (sh.cyc_db != 0) sh.tiles = tma_cyc_count_tiles(sh);       // active tiles only
   int sms = device_sm_count() - p.sm_reserve;
   if (sms < 8) sms = 8;
@@ -470,6 +470,11 @@ int debug_gemm_occupancy(int variant) {
 
 cudaError_t launch_gemm_store(cudaStream_t s, const GemmParams& p) { return launch_gemm_t<EPI_STORE>(s, p); }
 cudaError_t launch_gemm_sub(cudaStream_t s, const GemmParams& p) { return launch_gemm_t<EPI_SUB>(s, p); }
+cudaError_t launch_gemm_store_tma(cudaStream_t s, const GemmParams& p) {
+  if (p.M <= 0 || p.N <= 0) return cudaSuccess;
+  if (!tma_operand_ok(p.A, p.lda) || !tma_operand_ok(p.B, p.ldb)) return cudaErrorInvalidValue;
+  return launch_gemm_tma<EpiStoreTma>(s, p);
+}
 cudaError_t launch_gemm_store_lower(cudaStream_t s, const GemmParams& p) {
   if (p.M <= 0 || p.N <= 0) return cudaSuccess;
   if (tile_variant() == 0 && tma_operand_ok(p.A, p.lda) && tma_operand_ok(p.B, p.ldb))
@@ -578,7 +583,7 @@ DeviceCtx* lookahead_ctx() {
 
 cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long Mfull, long long N, int NB,
                             double* Linv_base, double* logdet, int* info, long long linv_stride,
-                            long long ident_row0) {
+                            long long ident_row0, double* fused_ws, bool want_L) {
   if (NB < PB) NB = PB;
   NB = (NB / PB) * PB;
   if (NB > LINV_BLOCKS * PB) NB = LINV_BLOCKS * PB;
@@ -592,20 +597,36 @@ cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long 
     if (e__ != cudaSuccess) return e__; \
   } while (0)
   const long long ls = (long long)PB * PB;          // one inverse block per 128 columns of the current panel
+  // single-launch panel solve (see kernels.cuh): needs the extra workspace and TMA-addressable operands
+  const bool fused = fused_ws != nullptr && la->fused_panel != 0 && tile_variant() == 0 && tma_operand_ok(A, lda);
+  double* const W = fused_ws;
+  double* const Pb = fused ? fused_ws + (size_t)FUSED_LD * FUSED_LD : nullptr;
+  const long long ldp = FUSED_LD;
   LA_CK(cudaEventRecord(la->ev_fork, s));
   LA_CK(cudaStreamWaitEvent(la->side, la->ev_fork, 0));
   for (long long c0 = 0; c0 < N; c0 += NB) {
     const long long c1 = (c0 + NB < N) ? c0 + NB : N;
     const int w = (int)(c1 - c0);
     const long long Mtot = active_rows(Mfull, ident_row0, c1);
-    // side: diagonal block (w x w) with its block inverses
+    const long long m = Mtot - c1;
+    // side: diagonal block (w x w) with its block inverses, then (fused) its full inverse W
     LA_CK(potrf_serial(la->side, A + c0 * lda + c0, lda, w, w, NB, Linv_base, logdet, info, ls, (int)c0, c0 == 0));
+    if (fused && m > 0) {
+      double* outs[1] = {W};
+      LA_CK(launch_assemble_inverse(la->side, A + c0 * lda + c0, lda, w, Linv_base, outs, 1, FUSED_LD, nullptr));
+    }
     LA_CK(cudaEventRecord(la->ev_diag, la->side));
     LA_CK(cudaStreamWaitEvent(s, la->ev_diag, 0));
-    // main: rows below the diagonal block <- rows * L_pp^-T by 128-block substitution
-    const long long m = Mtot - c1;
-    if (m > 0) {
-      double* R = A + c1 * lda + c0;
+    // main: rows below the diagonal block <- rows * L_pp^-T
+    if (m > 0 && fused) {
+      GemmParams t{};     // P = R W^T, contraction cut at W's diagonal, out of place (column tiles of one row block
+      t.A = A + c1 * lda + c0; t.lda = lda;     // read each other's input columns: in place would race)
+      t.B = W;                 t.ldb = FUSED_LD;
+      t.C = Pb;                t.ldc = ldp;
+      t.M = (int)m; t.N = w; t.K = w; t.lower = 0; t.k_upto_col = 1;
+      LA_CK(launch_gemm_store_tma(s, t));
+    } else if (m > 0) {
+      double* R = A + c1 * lda + c0;            // 128-block substitution, in place
       for (long long j0 = 0; j0 < w; j0 += PB) {
         const long long j1 = (j0 + PB < w) ? j0 + PB : w;
         GemmParams t{};
@@ -624,17 +645,27 @@ cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long 
         }
       }
     }
+    LA_CK(cudaEventRecord(la->ev_a, s));                    // panel p solved
+    if (m > 0 && fused) {
+      // copy back what somebody reads later: carried rows (>= N) always, the square rows of L only on request
+      const long long r_first = want_L ? c1 : (N > c1 ? N : c1);
+      if (r_first < Mtot)
+        LA_CK(cudaMemcpy2DAsync(A + r_first * lda + c0, (size_t)lda * 8, Pb + (r_first - c1) * ldp, (size_t)ldp * 8,
+                                (size_t)w * 8, (size_t)(Mtot - r_first), cudaMemcpyDeviceToDevice, s));
+    }
     if (c1 >= N) break;
+    // panel operands of the trailing updates: the panel buffer (fused) or the solved columns of A
+    const double* Pop = fused ? Pb : A + c1 * lda + c0;     // row 0 = global row c1
+    const long long ldo = fused ? ldp : lda;
     // Look-ahead split: the NEXT diagonal block (na x na, lower) is updated first, on the side stream, so that its
     // factorisation chain can start at once; everything else - including the rest of the next block column - is one
     // well-filled launch on the main stream that leaves a few SMs to the chain when the trailing matrix is small.
     const long long na = (c1 + NB < N) ? NB : N - c1;
-    LA_CK(cudaEventRecord(la->ev_a, s));                    // panel p solved (TRSM done on the main stream)
     LA_CK(cudaStreamWaitEvent(la->side, la->ev_a, 0));
     {
       GemmParams u{};
-      u.A = A + c1 * lda + c0; u.lda = lda;
-      u.B = A + c1 * lda + c0; u.ldb = lda;
+      u.A = Pop; u.lda = ldo;
+      u.B = Pop; u.ldb = ldo;
       u.C = A + c1 * lda + c1; u.ldc = lda;
       u.M = (int)na; u.N = (int)na; u.K = w; u.lower = 1;
       LA_CK(launch_gemm_sub(la->side, u));
@@ -644,8 +675,8 @@ cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long 
       // rows [cb, Mtot) x cols [c1, N): local row r may touch columns <= r + na (plain shifted diagonal = the
       // block-row-cyclic mask with one huge block)
       GemmParams u{};
-      u.A = A + cb * lda + c0; u.lda = lda;
-      u.B = A + c1 * lda + c0; u.ldb = lda;
+      u.A = Pop + (cb - c1) * ldo; u.lda = ldo;
+      u.B = Pop; u.ldb = ldo;
       u.C = A + cb * lda + c1; u.ldc = lda;
       u.M = (int)(Mtot - cb); u.N = (int)(N - c1); u.K = w; u.lower = 1;
       u.cyc_db = 1 << 30; u.cyc_p = 1; u.base_shift = (int)na;
@@ -659,6 +690,7 @@ cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long 
       if (instr().time_updates) instr_end_update(s);
     }
   }
+  // the side stream's last work (diagonal block of the last panel) was joined through ev_diag
 #undef LA_CK
   return cudaSuccess;
 }

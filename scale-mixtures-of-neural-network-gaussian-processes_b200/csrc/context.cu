@@ -46,9 +46,14 @@ Enter::Enter(cudaStream_t s) {
   cudaGetDevice(&prev);
   dev = prev;
   // the legacy / per-thread default streams belong to whatever device is current
+  // (not while the stream is being captured into a graph: cudaStreamGetDevice is not a capturable call and would
+  // invalidate the capture; a capture was begun on the current device anyway)
   if (s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     int sd = -1;
-    if (cudaStreamGetDevice(s, &sd) == cudaSuccess && sd >= 0) dev = sd;
+    if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone &&
+        cudaStreamGetDevice(s, &sd) == cudaSuccess && sd >= 0)
+      dev = sd;
   }
   if (dev != prev) cudaSetDevice(dev);
   ctx = &dctx_of(dev);
@@ -64,6 +69,7 @@ Enter::~Enter() {
 Instrumentation& instr() { return dctx().instr; }
 int& tile_variant() { return dctx().tile_variant; }
 int& lookahead_mode() { return dctx().lookahead; }
+int& gram_super_rows() { return dctx().gram_super; }
 int* lookahead_reserve() { return dctx().la_reserve; }
 long long*& potf2_clock_buffer() { return dctx().potf2_clk; }
 int device_sm_count() { return dctx().sms; }

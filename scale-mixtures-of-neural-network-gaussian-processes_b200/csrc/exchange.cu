@@ -19,41 +19,12 @@
 #include "gemm_core.cuh"
 #include "context.cuh"
 #include "kernels.cuh"
+#include "peer_signal.cuh"
 #include "tma_core.cuh"
 
 namespace smnngp {
 
 namespace {
-
-constexpr int MAX_PEERS = 8;
-
-struct PeerSignal {
-  unsigned long long* flag[MAX_PEERS];   // flag word of THIS source on every destination rank
-  unsigned long long seq;
-  unsigned int* counter;                 // device-local CTA counter (zero between launches)
-  int P;
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// called by ONE thread per CTA after the CTA's threads have fenced and synchronised
-__device__ __forceinline__ void signal_if_last_cta(const PeerSignal& sg) {
-  __threadfence_system();
-  const unsigned int prev = atomicAdd(sg.counter, 1u);
-  if (prev == gridDim.x - 1) {
-    *sg.counter = 0u;                    // next launch on this stream starts from zero
-    __threadfence_system();
-    for (int q = 0; q < sg.P; q++)
-      if (sg.flag[q] != nullptr) st_release_sys(sg.flag[q], sg.seq);
-  }
-}
 
 struct ScatterParams {
   GemmParams g;                 // A = panel rows R [m, w], B = W [w, w], C = local-order copy [m, ldc]
@@ -105,7 +76,7 @@ struct EpiScatterTma {
   static __device__ __forceinline__ void finish(const Params& p) {
     __threadfence_system();
     asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 math warps; the producer warps have left
-    if (threadIdx.x == 128) signal_if_last_cta(p.sig);
+    if (threadIdx.x == 128) signal_if_last_cta(p.sig, gridDim.x);
   }
 };
 
@@ -131,16 +102,7 @@ __global__ void __launch_bounds__(256) transpose_scatter_kernel(const double* __
   }
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    // gridDim.x * gridDim.y CTAs: count them all
-    __threadfence_system();
-    const unsigned int prev = atomicAdd(sp.sig.counter, 1u);
-    if (prev == gridDim.x * gridDim.y - 1) {
-      *sp.sig.counter = 0u;
-      __threadfence_system();
-      for (int q = 0; q < sp.sig.P; q++) st_release_sys(sp.sig.flag[q], sp.sig.seq);
-    }
-  }
+  if (threadIdx.x == 0) signal_if_last_cta(sp.sig, gridDim.x * gridDim.y);
 }
 
 __global__ void signal_kernel(PeerSignal sg) {
@@ -248,6 +210,24 @@ int smnngp_stage_scatter_inverse_f64(void* stream, const double* Ut, int64_t ldu
   transpose_scatter_kernel<<<grid, 256, 0, s>>>(Ut, ldu, (int)w, ldw, sp);
   instr().launches++;
   return cudaGetLastError() == cudaSuccess ? SMNNGP_OK : SMNNGP_ECUDA;
+}
+
+// W = inv(L) (row-major lower, pitch ldw) of the factored w x w block L (pitch ldl) from L and the inverses of its
+// 128 x 128 diagonal blocks, stored straight into the W buffer of every rank, then flag (trtri.cu)
+int smnngp_stage_assemble_inverse_f64(void* stream, const double* L, int64_t ldl, int64_t w, const double* linv_blocks,
+                                      void* const* dst_ptrs, int P, int64_t ldw, void* const* flag_ptrs,
+                                      int64_t flag_index, uint64_t seq, unsigned int* counter) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
+  if (!L || !linv_blocks || !dst_ptrs || P < 1 || P > MAX_PEERS || w <= 0 || !assemble_inverse_ok(L, ldl, (int)w, ldw))
+    return SMNNGP_EINVAL;
+  double* outs[MAX_PEERS] = {};
+  for (int q = 0; q < P; q++) outs[q] = static_cast<double*>(dst_ptrs[q]);
+  PeerSignal sg{};
+  if (flag_ptrs != nullptr && counter != nullptr) fill_signal(sg, flag_ptrs, P, flag_index, seq, counter);
+  return launch_assemble_inverse(s, L, ldl, (int)w, linv_blocks, outs, P, ldw, counter ? &sg : nullptr) == cudaSuccess
+             ? SMNNGP_OK
+             : SMNNGP_ECUDA;
 }
 
 int smnngp_stage_signal_f64(void* stream, void* const* flag_ptrs, int P, int64_t flag_index, uint64_t seq) {

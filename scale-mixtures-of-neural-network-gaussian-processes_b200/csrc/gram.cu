@@ -3,6 +3,7 @@
 // applies the whole L-layer ReLU arc-cosine / erf recursion in registers, so every kernel entry is written to
 // HBM exactly once.  Symmetric case: only tiles on or below the diagonal are computed (optionally mirrored).
 #include "gemm_core.cuh"
+#include "context.cuh"
 #include "kernels.cuh"
 #include "nngp_math.cuh"
 #include "tma_core.cuh"
@@ -267,6 +268,12 @@ cudaError_t launch_gram_tma(cudaStream_t s, const GramParams& p) {
   if (!make_tmap(&ma, p.X1, p.N, p.D, p.ld1, TM_BM) || !make_tmap(&mb, p.X2, p.M, p.D, p.ld2, TM_BN))
     return cudaErrorInvalidValue;
   TmaShape sh{p.N, p.M, p.D, p.symmetric, count_tiles<TileTma>(p.N, p.M, p.symmetric), 0, 1, 0};
+  // L2-aware rasterisation once a tile row's B operand no longer fits the L2 next to everything else (~40 MB)
+  const int sr = gram_super_rows();
+  if (sr > 0 && (double)p.M * (double)p.D * 8.0 >= (double)dctx().gram_super_min_bytes) {
+    sh.super_rows = sr;
+    sh.tiles = tma_super_count_tiles(p.N, p.M, p.symmetric, sr);
+  }
   cudaError_t e = p.act == ACT_RELU ? launch_tma_gemm<EpiGramTma<ACT_RELU>>(s, ma, mb, sh, p, device_sm_count())
                                     : launch_tma_gemm<EpiGramTma<ACT_ERF>>(s, ma, mb, sh, p, device_sm_count());
   instr().launches++;

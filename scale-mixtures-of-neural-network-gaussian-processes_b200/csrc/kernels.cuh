@@ -13,6 +13,8 @@ int& tile_variant();
 int debug_gemm_occupancy(int variant);
 // 1 (default): the fused factorisation runs the next panel's diagonal block on a side stream (look-ahead)
 int& lookahead_mode();
+// super-tile height (in 128-row tiles) of the Gram kernel's L2-aware tile walk; 0 = plain row-major walk
+int& gram_super_rows();
 int* lookahead_reserve();
 // diagnostic: when non-null, thread 0 of the diagonal-block kernel stores clock64() at its phase boundaries
 long long*& potf2_clock_buffer();
@@ -49,6 +51,7 @@ struct GemmParams {
   int cyc_db, cyc_p, base_shift;
   int sm_reserve;     // persistent kernel leaves this many SMs free (look-ahead work on another stream)
   int k_from_row;     // 1: contraction of the tile whose first row is r0 starts at k = r0 (operands upper triangular)
+  int k_upto_col;     // 1: B is lower triangular - the contraction of the tile whose first column is c0 stops at c0 + 64
 };
 
 // largest active column of local row r (rows are non-decreasing in this limit)
@@ -85,11 +88,32 @@ cudaError_t launch_gemm_sub(cudaStream_t s, const GemmParams& p);
 // ident_row0 >= 0: rows ident_row0 .. ident_row0 + N - 1 of A start as the identity (the caller wrote it) and end up
 // as U = L^-T (upper triangular).  Identity row i stays e_i until the panel that contains column i, so while
 // factoring panel [c0, c1) only carried rows below ident_row0 + c1 are touched (N^3/3 flop instead of N^3).
+// fused_ws (optional, fused_ws_doubles(Mtot) doubles): enables the single-launch panel solve.  Per outer panel the rows below the diagonal block are then solved OUT OF PLACE into the
+// panel buffer (one TMA GEMM with the block's full inverse) and the trailing updates read the panel buffer; carried
+// rows (>= N) are copied back into A, the square rows of L only when want_L is set - the fused LML / predictive
+// paths never read them.
 cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long Mtot, long long N, int NB,
                             double* Linv_ws, double* logdet, int* info, long long linv_stride = 0,
-                            long long ident_row0 = -1);
+                            long long ident_row0 = -1, double* fused_ws = nullptr, bool want_L = true);
 // C = A B^T, lower part only, C does not alias the operands (TMA-fed persistent kernel when the operands allow)
 cudaError_t launch_gemm_store_lower(cudaStream_t s, const GemmParams& p);
+// C = A B^T out of place on the TMA core (p.lower / p.k_upto_col honoured); cudaErrorInvalidValue if an operand is
+// not TMA-addressable (16-byte aligned base, even pitch)
+cudaError_t launch_gemm_store_tma(cudaStream_t s, const GemmParams& p);
+
+// ---- full inverse of a panel's diagonal block (trtri.cu) -----------------------------------------------------
+struct PeerSignal;
+bool assemble_inverse_ok(const double* L, long long ldl, int w, long long ldw);
+// W [w, ldw] = inv(L) (lower, zero above the diagonal inside the diagonal blocks) from the factored block L and the
+// inverses of its 128 x 128 diagonal blocks; stored to out_ptrs[0 .. P) (peer buffers); sig != nullptr: the last CTA
+// raises the flags it describes
+cudaError_t launch_assemble_inverse(cudaStream_t s, const double* L, long long ldl, int w, const double* linv_blocks,
+                                    double* const* out_ptrs, int P, long long ldw, const PeerSignal* sig);
+
+// doubles of the extra workspace of potrf_trapezoid's single-launch panel solve for a trapezoid of Mtot rows:
+// W (512 x 512) + the out-of-place panel buffer (Mtot x 512)
+constexpr int FUSED_LD = LINV_BLOCKS * PB;
+inline size_t fused_ws_doubles(long long Mtot) { return (size_t)FUSED_LD * FUSED_LD + (size_t)Mtot * FUSED_LD; }
 
 // ---- reductions / closed forms ---------------------------------------------------------------------------
 cudaError_t launch_sumsq(cudaStream_t s, const double* z, long long n, double* out);

@@ -52,7 +52,24 @@ struct TmaShape {
   // the fragments they loaded and add the result to the address of the stage-release arrive: ptxas cannot see the
   // value of a kernel parameter, so the arrive carries a true data dependency on the loads (see tma_gemm_kernel).
   unsigned int zero;
+  // > 0: L2-aware rasterisation.  Tiles are enumerated super-tile by super-tile (super_rows x 2 super_rows tiles =
+  // a square of 128 super_rows elements; lower == 1: block-triangular list of super-tiles), row-major inside.  The
+  // ~2 x #SM tiles in flight at any time then cover 2-3 super-tiles (a few MB of operand rows, L2 resident) instead
+  // of one long strip of a tile row whose B operand streams from DRAM again for every tile row.  Tile slots outside
+  // the matrix or above the diagonal are skipped (producer and math warps decode alike).
+  int super_rows;
 };
+
+__host__ __device__ __forceinline__ long long tma_super_count_tiles(int M, int N, int lower, int sr) {
+  const long long ntm = (M + TM_BM - 1) / TM_BM, ntn = (N + TM_BN - 1) / TM_BN;
+  const long long nsr = (ntm + sr - 1) / sr, nsc = (ntn + 2 * sr - 1) / (2 * sr);
+  const long long per = 2ll * sr * sr;
+  if (!lower) return nsr * nsc * per;
+  // block-triangular: super row I holds super columns 0 .. min(I, nsc - 1)
+  long long cnt = 0;
+  for (long long I = 0; I < nsr; I++) cnt += (I + 1 < nsc ? I + 1 : nsc);
+  return cnt * per;
+}
 
 // Block-row-cyclic mask: number of column tiles of row tile ti that touch the active region (a prefix of the row,
 // the limit grows with the row).  Only these tiles are enumerated, so the static tile -> CTA assignment stays
@@ -76,11 +93,40 @@ struct TileCursor {
   int ti = 0;
   long long base = 0;      // active tiles in rows < ti
 };
-__device__ __forceinline__ void tma_decode(const TmaShape& sh, long long t, int ntn, TileCursor& cur, int& ti,
+// returns false for an enumeration slot that holds no tile (super-tile rasterisation only)
+__device__ __forceinline__ bool tma_decode(const TmaShape& sh, long long t, int ntn, TileCursor& cur, int& ti,
                                            int& tj) {
+  if (sh.super_rows > 0) {
+    const int sr = sh.super_rows, sc = 2 * sr;
+    const int per = sr * sc;
+    const long long S = t / per;
+    const int within = (int)(t - S * per);
+    const int ntm = (sh.M + TM_BM - 1) / TM_BM;
+    long long I, J;
+    if (sh.lower) {
+      const long long nsc = (ntn + sc - 1) / sc;
+      const long long tri = nsc * (nsc + 1) / 2;          // super rows 0 .. nsc-1 are triangular, later ones full
+      if (S < tri) {
+        I = (long long)((sqrt(8.0 * (double)S + 1.0) - 1.0) * 0.5);
+        while (I * (I + 1) / 2 > S) --I;
+        while ((I + 1) * (I + 2) / 2 <= S) ++I;
+        J = S - I * (I + 1) / 2;
+      } else {
+        I = nsc + (S - tri) / nsc;
+        J = (S - tri) % nsc;
+      }
+    } else {
+      const long long nsc = (ntn + sc - 1) / sc;
+      I = S / nsc;
+      J = S % nsc;
+    }
+    ti = (int)(I * sr) + within / sc;
+    tj = (int)(J * sc) + within % sc;
+    return ti < ntm && tj < ntn && (!sh.lower || tj <= 2 * ti + 1);
+  }
   if (sh.cyc_db == 0) {
     decode_tile<2>(t, ntn, sh.lower, ti, tj);
-    return;
+    return true;
   }
   int cnt = tma_cyc_row_tiles(sh, cur.ti, ntn);
   while (t >= cur.base + cnt) {
@@ -89,6 +135,7 @@ __device__ __forceinline__ void tma_decode(const TmaShape& sh, long long t, int 
   }
   ti = cur.ti;
   tj = (int)(t - cur.base);
+  return true;
 }
 
 // ---- host: tensor map for a row-major [rows, inner] FP64 operand (row pitch ld doubles) ---------------------
@@ -212,7 +259,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       TileCursor cur;
       for (long long t = 2ll * blockIdx.x + g; t < sh.tiles; t += stride) {
         int ti, tj;
-        tma_decode(sh, t, ntn, cur, ti, tj);
+        if (!tma_decode(sh, t, ntn, cur, ti, tj)) continue;
         const int r0 = ti * TM_BM, c0 = tj * TM_BN;
         const int kt_end = tma_kt_end(sh, KT, c0);
         for (int kt = sh.k_from_row ? r0 / BK : 0; kt < kt_end; kt++) {
@@ -242,7 +289,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   TileCursor cur;
   for (long long t = 2ll * blockIdx.x + g; t < sh.tiles; t += stride) {
     int ti, tj;
-    tma_decode(sh, t, ntn, cur, ti, tj);
+    if (!tma_decode(sh, t, ntn, cur, ti, tj)) continue;
     double acc[MI][NI][2];
 #pragma unroll
     for (int mi = 0; mi < MI; mi++)

@@ -154,7 +154,7 @@ def potrf_(a: torch.Tensor, n_cols=None):
     n = a.shape[1] if n_cols is None else n_cols
     info = torch.zeros(1, dtype=torch.int32, device=a.device)
     logdet = torch.zeros(1, dtype=torch.float64, device=a.device)
-    ws_bytes = lib.smnngp_potrf_workspace_bytes(n)
+    ws_bytes = lib.smnngp_potrf_workspace_bytes(max(m, n))       # rows: sizes the panel buffer of the fused solve
     ws = _workspace(ws_bytes, a.device)
     rc = lib.smnngp_potrf_trapezoid_f64(_stream(a.device), _p(a), m, n, a.stride(0), _p(logdet), _p(info), _p(ws),
                                         ws_bytes)

@@ -301,22 +301,38 @@ class DistributedLML:
         self.lay = BlockRowCyclic(self.n + self.n_extra, self.n, self.world, self.rank, self.db)
         self.ld = _cdiv(self.n, 16) * 16
         self.mloc = self.lay.local_rows()
-        self.a = self.be.empty(max(self.mloc, 1), self.ld)
+        self.a = self.be.empty(1, 16)             # device marker until the driver is chosen (row shard: see below)
         nblk = self.db // PB
-        self.diag = self.be.empty(self.db * self.db + nblk * PB * PB)
         # largest per-rank panel piece over all panels (panel p -> rows in blocks >= p + 1)
         self.max_m = max(self.lay.rows_from_block(1, r)[1] for r in range(self.world)) if self.world > 1 else 0
         self._nccl_bufs = False
         # panel exchange: "peer" = stores into the other ranks' buffers over NVLink (csrc/exchange.cu), "nccl" =
         # broadcast + all-gather (also the path the CPU suite drives under gloo with the NumPy backend)
-        peer_ok = self.a.is_cuda and isinstance(self.be, CudaBackend) and 1 < self.world <= 8
+        # (a one-rank job may use it too when asked for explicitly: emulate=(1, 0) is the real computation)
+        peer_ok = self.a.is_cuda and isinstance(self.be, CudaBackend) and (1 < self.world <= 8 or self.emulate)
         if exchange == "auto":
             exchange = os.environ.get("SMNNGP_EXCHANGE", "peer" if peer_ok else "nccl")
         if exchange == "peer" and not peer_ok:
             raise ValueError("exchange='peer' needs CUDA, the C-ABI backend and 2..8 ranks")
         self.exchange = exchange
         self.px = None
-        if exchange == "peer":
+        self.mg = None
+        # exchange == "peer": the whole evaluation is ONE C call per rank (csrc/multigpu.cu, smnngp_lml_mg_f64); the
+        # Python panel loop below remains for the NCCL exchange, the NumPy backend of the CPU suite, the predictive
+        # driver (DistributedPredict) and as a cross-check (SMNNGP_MG_DRIVER=python)
+        use_c = (exchange == "peer" and type(self) is DistributedLML and
+                 os.environ.get("SMNNGP_MG_DRIVER", "c") == "c")
+        if use_c:
+            try:
+                self._create_mg(group)
+            except PeerUnavailable as e:
+                import warnings
+                warnings.warn(f"smnngp: {e}; using the NCCL panel exchange")
+                self.exchange = exchange = "nccl"
+        if self.mg is None:                       # Python panel loop: the row shard lives here
+            self.a = self.be.empty(max(self.mloc, 1), self.ld)
+            self.diag = self.be.empty(self.db * self.db + nblk * PB * PB)
+        if exchange == "peer" and self.mg is None:
             try:
                 self.px = PeerExchange(self.be.lib, self.a.device, self.world, self.rank, group, self.n, self.db,
                                        emulate=self.emulate)
@@ -324,8 +340,7 @@ class DistributedLML:
                 import warnings
                 warnings.warn(f"smnngp: {e}; using the NCCL panel exchange")
                 self.exchange = exchange = "nccl"
-        if exchange == "peer":
-            self.tdiag = self.be.empty(2 * self.db * self.db)            # owner's factorisation scratch [2w, w]
+        if exchange == "peer" and self.mg is None:
             self.linv4 = self.be.empty(nblk * PB * PB)
             self.ploc = [self.be.empty(max(self.mloc, 1), self.db) for _ in range(2)]
             self.counters = torch.zeros(8, dtype=torch.int32, device=self.a.device)
@@ -345,8 +360,61 @@ class DistributedLML:
         self.reserve_below_s = float(os.environ.get("SMNNGP_RESERVE_BELOW_MS", "18")) * 1e-3
         self.sm_reserve_auto = "SMNNGP_SM_RESERVE" not in os.environ
 
+    def _create_mg(self, group):
+        """one smnngp_mg handle per rank; the 64-byte IPC handles travel through one all-gather"""
+        lib, dev = self.be.lib, self.a.device
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            ok = lib.smnngp_mg_create(C.byref(h), self.rank, self.world, self.n, self.db) == 0
+            handle = (C.c_ubyte * 64)()
+            if ok:
+                lib.smnngp_mg_ipc_handle(h, handle)
+            if self.emulate or self.world == 1:
+                if not ok:
+                    raise RuntimeError("smnngp_mg_create failed: " + lib.smnngp_mg_last_error().decode())
+                if self.emulate:
+                    lib.smnngp_mg_connect_emulated(h)
+            else:
+                # every rank takes part in both collectives even if its own step failed, so a failure anywhere makes
+                # ALL ranks fall back to the NCCL exchange together
+                mine = torch.tensor(list(handle) if ok else [0] * 64, dtype=torch.uint8, device=dev)
+                allh = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(allh, mine, group=group)
+                flat = torch.cat(allh).cpu().numpy().tobytes()
+                if ok and all(any(t.cpu().tolist()) for t in allh):
+                    ok = lib.smnngp_mg_connect_ipc(h, flat) == 0
+                else:
+                    ok = False
+                flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+                torch.cuda.synchronize(dev)
+                if int(flag.item()) == 0:
+                    if h.value:
+                        lib.smnngp_mg_destroy(h)
+                    raise PeerUnavailable("CUDA IPC peer memory could not be set up on every rank")
+            lib.smnngp_mg_set_timeout(h, float(os.environ.get("SMNNGP_PEER_TIMEOUT_S", "20")))
+            if "SMNNGP_SM_RESERVE" in os.environ:
+                lib.smnngp_mg_set_sm_reserve(h, int(os.environ["SMNNGP_SM_RESERVE"]))
+        self.mg = h                               # the row shard lives inside the handle
+
+    LABELS = ("diag", "bcast", "trsm", "gather", "main_start", "update_a", "update_b", "start")
+
+    def timeline_read(self, cap=8192):
+        """[(panel, label, ms since the first mark)] recorded by the C driver after ``enable_timeline()``"""
+        pan, lab, ms = (C.c_int * cap)(), (C.c_int * cap)(), (C.c_double * cap)()
+        k = self.be.lib.smnngp_mg_timeline_read(self.mg, cap, pan, lab, ms)
+        return [(pan[i], self.LABELS[lab[i]], ms[i]) for i in range(k)]
+
+    def enable_timeline(self, on=True):
+        self.be.lib.smnngp_mg_timeline(self.mg, 1 if on else 0)
+
     def close(self):
         """release the peer-visible buffers (CUDA IPC mappings + the local cudaMalloc region)"""
+        if self.mg is not None:
+            with torch.cuda.device(self.a.device):
+                torch.cuda.synchronize(self.a.device)
+                self.be.lib.smnngp_mg_destroy(self.mg)
+            self.mg = None
         if self.px is not None:
             if self.a.is_cuda:
                 torch.cuda.synchronize(self.a.device)
@@ -418,15 +486,14 @@ class DistributedLML:
         seq = self.seq_base + p + 1
         ck = self.be._ck
         if self.rank == owner:
+            # diagonal block factored in place (L_pp + the inverses of its 128-blocks), then its full inverse W is
+            # assembled straight into every rank's W buffer and the W-ready flag is raised (csrc/trtri.cu)
             lo = lay.local_offset(p)
             blk = self.a[lo:lo + w, c0:c1]
-            ck(lib.smnngp_stage_factor_diag_inv_f64(s, C.c_void_p(blk.data_ptr()), blk.stride(0), w,
-                                                    C.c_void_p(self.tdiag.data_ptr()), C.c_void_p(self.linv4.data_ptr()),
-                                                    C.c_void_p(sums.data_ptr()), C.c_void_p(info.data_ptr()), c0),
-               "factor_diag_inv")
-            ck(lib.smnngp_stage_scatter_inverse_f64(s, C.c_void_p(self.tdiag.data_ptr() + w * w * 8), w, w, px.w_ptrs,
-                                                    P, db, px.flag_ptrs, 0, seq,
-                                                    C.c_void_p(self.counters.data_ptr())), "scatter_inverse")
+            self.be.factor_diag(blk, self.linv4, sums[0:1], info, c0)
+            ck(lib.smnngp_stage_assemble_inverse_f64(s, C.c_void_p(blk.data_ptr()), blk.stride(0), w,
+                                                     C.c_void_p(self.linv4.data_ptr()), px.w_ptrs, P, db, px.flag_ptrs,
+                                                     0, seq, C.c_void_p(self.counters.data_ptr())), "assemble_inverse")
         self._mark(p, "diag")
         if not self.emulate or self.rank == owner:           # (dry-run: nobody else is there to raise flags)
             ck(lib.smnngp_stage_wait_flags_f64(s, px.flags_local, 0, 1, seq, self.wait_timeout_s,
@@ -531,6 +598,16 @@ class DistributedLML:
     def lml(self, x, y, hp, kind="student_t"):
         """SPR.loss pieces: (out[4] = {log p, loss, sum log L_ii, ||L^-1 y||^2}, info), identical on every rank."""
         be, lay, n, db, P = self.be, self.lay, self.n, self.db, self.world
+        if self.mg is not None:                                    # one C call per rank (csrc/multigpu.cu)
+            nh, act, arch = self.spec.ids()
+            x, y = x.contiguous(), y.contiguous()
+            out = be.empty(4)
+            info = be.zeros(1, dtype=torch.int32)
+            rc = be.lib.smnngp_lml_mg_f64(self.mg, be._s(), be._p(x), be._p(y), x.shape[1], nh, act, arch, be._p(hp),
+                                          KIND[kind], SHIFT[self.gram_shift], be._p(out), be._p(info))
+            if rc != 0:
+                raise RuntimeError("smnngp_lml_mg_f64 failed: " + be.lib.smnngp_mg_last_error().decode())
+            return out, info
         sums, info, npanels = self._factor(x, y, hp)
         # z = (L^-1 y)^T sits in global row N on its owner
         bn = n // db

@@ -95,13 +95,37 @@ def test_emulated_rank_schedule_runs_on_one_gpu():
     n, d = 3000, 8
     x, y, *_ = regression_data(n, d)
     job = DistributedLML(n, d, sm.StackSpec(3, "relu", "mlp"), "cuda", block=256, emulate=(4, 1))
-    assert job.exchange == "peer" and job.world == 4 and job.rank == 1
-    job.timeline = []
+    assert job.exchange == "peer" and job.world == 4 and job.rank == 1 and job.mg is not None
+    job.enable_timeline()
     job.lml(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), sm.make_hp(**hp))
     torch.cuda.synchronize()
-    labels = {lab for _, lab, _ in job.timeline}
+    labels = {lab for _, lab, _ in job.timeline_read()}
     assert {"main_start", "update_a", "update_b", "diag", "trsm", "gather"} <= labels
-    job.px.close()
+    job.close()
+
+
+@pytest.mark.parametrize("driver", ["c", "python"])
+@pytest.mark.parametrize("n,db", [(700, 128), (2500, 512), (3000, 256)])
+def test_single_rank_peer_drivers_match_oracle(n, db, driver, monkeypatch):
+    """the peer-store pipeline (owner chain with the assembled inverse, fused solve + scatter, flags, reduce slots) at
+    world size 1, once through the C driver (smnngp_lml_mg_f64) and once through the Python panel loop"""
+    import torch
+    import smnngp_b200 as sm
+    from smnngp_b200.distributed import DistributedLML
+    from tests.synth import regression_data, DEFAULT_HP as hp
+    monkeypatch.setenv("SMNNGP_MG_DRIVER", driver)
+    d = 8
+    x, y, *_ = regression_data(n, d)
+    # emulate=(1, 0) = a one-rank job whose only peer is itself: results are the real ones
+    job = DistributedLML(n, d, sm.StackSpec(3, "relu", "mlp"), "cuda", block=db, emulate=(1, 0), exchange="peer")
+    assert (job.mg is not None) == (driver == "c")
+    xd, yd, hpd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), sm.make_hp(**hp)
+    out, info = job.lml(xd, yd, hpd)
+    out2, _ = job.lml(xd, yd, hpd)
+    ref = _ref(n, d, "student_t")
+    assert int(info.item()) == 0 and out2.cpu().tolist() == out.cpu().tolist()
+    assert abs(out[1].item() - ref) <= 1e-8 * abs(ref)
+    job.close()
 
 
 def _predict_worker(rank, world, port, n, t, c, d, db, q, exchange):

@@ -72,6 +72,35 @@ def test_gram_cross(sm, n, m, d, act, arch):
     assert np.abs(k - ref).max() / np.abs(ref).max() <= GRAM_TOL
 
 
+@pytest.mark.parametrize("sr", [1, 2, 3])
+def test_gram_super_tile_walk(sm, sr):
+    """L2-aware rasterisation of the Gram kernel (super-tiles of sr x 2 sr tiles) forced on at small sizes: ragged
+    edges, more super-tile slots than tiles, symmetric (block-triangular list) and cross (rectangular) cases"""
+    import torch
+    lib = sm._lib.load()
+    lib.smnngp_set_gram_super_rows(sr, 0)
+    try:
+        hp, hpd = _hp(sm, b_std=0.2)
+        spec = sm.StackSpec(2, "relu", "mlp")
+        kw = _kw(hp, 2, "relu", "mlp")
+        for n in (1000, 1153, 130):
+            x, *_ = regression_data(n, 16, seed=n)
+            ref = orc.nngp_gram(x, **kw)
+            xd = torch.from_numpy(x).cuda()
+            k = sm.device.gram(xd, spec=spec, hp=hpd).cpu().numpy()
+            assert np.abs(k - ref).max() <= GRAM_TOL * np.abs(ref).max()
+            kl = sm.device.gram(xd, spec=spec, hp=hpd, shift="eps_abs", lower_only=True).cpu().numpy()
+            assert np.all(np.triu(kl, 1) == 0.0)
+            assert np.abs(kl - np.tril(ref + hp["eps"] * np.eye(n))).max() <= GRAM_TOL * np.abs(ref).max()
+        x1, *_ = regression_data(700, 16, seed=1)
+        x2, *_ = regression_data(1333, 16, seed=2)
+        ref = orc.nngp_gram(x1, x2, **kw)
+        k = sm.device.gram(torch.from_numpy(x1).cuda(), torch.from_numpy(x2).cuda(), spec=spec, hp=hpd).cpu().numpy()
+        assert np.abs(k - ref).max() <= GRAM_TOL * np.abs(ref).max()
+    finally:
+        lib.smnngp_set_gram_super_rows(8, -1)
+
+
 def test_gram_duplicate_and_zero_rows(sm):
     """edge cases of the arc-cosine step: identical rows (s -> 0) and all-zero rows (atan2(0, 0) -> pi/2 fill)."""
     import torch
@@ -88,7 +117,10 @@ def test_gram_duplicate_and_zero_rows(sm):
         assert np.abs(k - ref).max() <= GRAM_TOL * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("n,extra", [(1, 0), (100, 0), (128, 1), (129, 3), (300, 0), (1000, 17), (2500, 1)])
+@pytest.mark.parametrize("n,extra", [(1, 0), (100, 0), (128, 1), (129, 3), (300, 0), (1000, 17), (2500, 1),
+                                     # outer panels of 256 / 512 columns: look-ahead + single-launch panel solve with the
+                                     # assembled block inverse (2 / 4 diagonal blocks), ragged last panel, carried rows
+                                     (4000, 0), (4100, 3), (8704, 2), (9000, 5)])
 def test_potrf_vs_lapack(sm, n, extra):
     import torch
     rng = np.random.default_rng(n)
@@ -123,6 +155,32 @@ def test_potrf_not_positive_definite(sm):
     logdet, info = sm.device.potrf_(ad)
     assert int(info.item()) == 201          # LAPACK convention: 1 + first bad pivot
     assert np.isnan(ad.cpu().numpy()[250, 250])
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+def test_potrf_fused_panel_matches_block_substitution(sm, fused):
+    """the single-launch panel solve (full inverse of the diagonal block, out of place) and the round-1 in-place
+    128-block substitution are two evaluations of the same factorisation: both must match LAPACK, also when the
+    matrix is not positive definite in a late panel (NaN + info, nothing raises)"""
+    import torch
+    n = 5000
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal((n, n + 8))
+    a = b @ b.T / (n + 8) + 1e-3 * np.eye(n)
+    lib = sm._lib.load()
+    lib.smnngp_set_fused_panel(fused)
+    try:
+        ad = torch.from_numpy(a.copy()).cuda()
+        logdet, info = sm.device.potrf_(ad)
+        L = sla.cholesky(a, lower=True)
+        assert int(info.item()) == 0
+        assert np.abs(np.tril(ad.cpu().numpy()) - L).max() / np.abs(L).max() <= 1e-11
+        a[4500, 4500] = -1.0
+        ad = torch.from_numpy(a.copy()).cuda()
+        logdet, info = sm.device.potrf_(ad)
+        assert int(info.item()) == 4501 and np.isnan(ad.cpu().numpy()[4900, 4800])
+    finally:
+        lib.smnngp_set_fused_panel(1)
 
 
 @pytest.mark.parametrize("n,d,L,act,arch,kind", [
