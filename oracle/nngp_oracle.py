@@ -138,7 +138,14 @@ def nngp_gram(x1, x2=None, *, num_hiddens, act="relu", w_std=1.0, b_std=0.0, las
             raise KeyError("Unsupported act '{}'".format(act))
         if arch not in ARCHS:
             raise ValueError(f"Unsupported network '{arch}'")
-        k = (x1 @ x2.T) / d
+        # X1.X2^T / D in row blocks written straight into the output: one big `x1 @ x2.T` segfaults inside NumPy /
+        # OpenBLAS once the result has more than 2^31 elements (N >= 46 341), and the blocks avoid a second N x M array
+        k = np.empty((x1.shape[0], x2.shape[0]), dtype=np.float64)
+        x2t = x2.T
+        for r0 in range(0, x1.shape[0], row_block):
+            r1 = min(r0 + row_block, x1.shape[0])
+            np.matmul(x1[r0:r1], x2t, out=k[r0:r1])
+        k /= d
         rc = _c_recursion().nngp_recursion_inplace(k.ctypes.data, k.shape[0], k.shape[1], q1.ctypes.data,
                                                    q2.ctypes.data, int(num_hiddens), ACTS.index(act),
                                                    ARCHS.index(arch), float(w_std), float(b_std), float(last_w_std))

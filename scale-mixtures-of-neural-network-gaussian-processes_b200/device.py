@@ -449,6 +449,19 @@ class GridSearch:
         return mean, var, 2.0 * out[0], out[1], info
 
 
+    def sweep_eps(self, eps_list, hp, group=None):
+        """find.py:141 `for eps in eps_list`: every regulariser of the sweep for the scalars in ``hp`` (its eps entry is
+        replaced), one epsilon per GPU when a process group is up (replica parallelism, see distributed.sweep_eps)."""
+        from .distributed import sweep_eps
+
+        def evaluate(eps):
+            h = hp.clone()
+            h[3] = eps
+            return self.point(h)
+
+        return sweep_eps(eps_list, evaluate, t=self.t, device=self.y.device, group=group)
+
+
 def set_panel_width(nb: int):
     _lib.load().smnngp_set_panel_width(int(nb))
 

@@ -795,3 +795,37 @@ class _NullCtx:
 
     def __exit__(self, *exc):
         return False
+
+
+def sweep_eps(eps_list, evaluate, *, t, device, group=None):
+    """The epsilon sweep of the reference's grid search (experiments/regression/find.py:20, :141: eleven regularisers
+    per (w_std, b_std) point, each a new pair of factorisations of the SAME Gram matrix) as replica parallelism: the
+    path does not shard below one factorisation here, so rank r evaluates eps_list[r::world] on its own GPU (its own
+    cached base Gram, no data-path collective) and one all-gather of the small results makes every rank see all of them.
+
+    evaluate(eps) -> (mean [T], var [T], logdet, quad, info) on `device` (``GridSearch.point`` with that eps).
+    Returns a list aligned with eps_list of (mean [T], var [T], logdet, quad, info) device tensors / Python numbers."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n_eps = len(eps_list)
+    per = _cdiv(n_eps, world)
+    # fixed-size slots so one all_gather_into_tensor moves everything: [mean | var | logdet quad info]
+    mine = torch.zeros((per, 2 * t + 3), dtype=torch.float64, device=device)
+    for k, i in enumerate(range(rank, n_eps, world)):
+        mean, var, logdet, quad, info = evaluate(float(eps_list[i]))
+        mine[k, :t] = mean
+        mine[k, t:2 * t] = var
+        mine[k, 2 * t] = logdet
+        mine[k, 2 * t + 1] = quad
+        mine[k, 2 * t + 2] = info.to(torch.float64).reshape(()) if torch.is_tensor(info) else float(info)
+    if world > 1:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)                 # (list form: also available under gloo)
+        allr = torch.stack(parts)
+    else:
+        allr = mine[None]
+    out = []
+    for i in range(n_eps):
+        row = allr[i % world, i // world]
+        out.append((row[:t], row[t:2 * t], float(row[2 * t]), float(row[2 * t + 1]), int(row[2 * t + 2])))
+    return out

@@ -171,3 +171,46 @@ def test_layout_bookkeeping():
                 want = sum(lay.block_rows(b) for b in lay.local_blocks() if b >= gb)
                 assert cnt == want and o == lay.local_rows() - want
         assert (seen == 1).all()
+
+
+def _sweep_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from smnngp_b200.distributed import sweep_eps
+        t = 5
+        calls = []
+
+        def evaluate(eps):                       # stand-in for GridSearch.point: results are functions of eps only
+            calls.append(eps)
+            base = torch.arange(t, dtype=torch.float64)
+            return base * eps, base + eps, 10.0 * eps, 100.0 * eps, torch.tensor([0 if eps < 1.0 else 7])
+
+        eps_list = [1e-6 * 10 ** (0.5 * k) for k in range(11)] + [2.0]     # find.py:20 has eleven
+        res = sweep_eps(eps_list, evaluate, t=t, device="cpu")
+        q.put((rank, calls, [(m.tolist(), v.tolist(), ld, qd, info) for m, v, ld, qd, info in res], eps_list))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_eps_sweep_replicas(world):
+    """one epsilon per rank (experiments/regression/find.py:141): every rank evaluates only its share and sees all results"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + world
+    procs = [ctx.Process(target=_sweep_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, calls, res, eps_list in got:
+        assert calls == eps_list[rank::world]
+        assert len(res) == len(eps_list)
+        for eps, (m, v, ld, qd, info) in zip(eps_list, res):
+            assert m == [k * eps for k in range(5)] and v == [k + eps for k in range(5)]
+            assert ld == 10.0 * eps and qd == 100.0 * eps and info == (0 if eps < 1.0 else 7)
