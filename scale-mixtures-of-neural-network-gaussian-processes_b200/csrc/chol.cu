@@ -164,7 +164,12 @@ cudaError_t launch_gemm_t(cudaStream_t s, const GemmParams& p) {
   if (p.M <= 0 || p.N <= 0) return cudaSuccess;
   // The TRSM runs IN PLACE (C aliases A): a CTA must own whole rows of the <= 128-column panel, otherwise one
   // column tile could overwrite rows a sibling tile is still reading -> always the 128 x 128 tile for EPI_STORE.
+  if (EPI == EPI_STORE && p.M <= 1024 && tile_variant() == 0) return launch_gemm_cfg<TileSmallWide, EPI>(s, p);
   if (EPI == EPI_STORE || tile_variant() == 1) return launch_gemm_cfg<TileBig, EPI>(s, p);
+  // fewer 128 x 64 tiles than the persistent kernel has math groups on ~1/3 of the GPU: 64 x 64 tiles, one per CTA
+  if (tile_variant() == 0 && p.cyc_db == 0 && !p.k_from_row && !p.k_upto_col &&
+      count_tiles<TileTma>(p.M, p.N, p.lower) < 96)
+    return launch_gemm_cfg<TileSmall, EPI>(s, p);
   if (tile_variant() == 0 && tma_operand_ok(p.A, p.lda) && tma_operand_ok(p.B, p.ldb)) return launch_gemm_sub_tma(s, p);
   return launch_gemm_cfg<TilePair, EPI>(s, p);
 }
@@ -311,12 +316,16 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
   __syncthreads();
   PF_CLK();   // 1: staged
 
+  // In-CTA look-ahead: the serial part (warp 0 factoring + inverting a 16 x 16 diagonal block in registers, ~2.8 us)
+  // used to alternate with the panel / trailing-update phases of the other warps.  Now, once block b's panel is solved,
+  // warp 0 updates ONLY the next diagonal block and factors it while warps 1..7 apply the rest of block b's trailing
+  // update - the update hides under the pivot chain instead of adding to it.
   int bad = 0;
+  if (warp == 0) diag_factor_invert(G, Mi, lane, 0, bad);
+  __syncthreads();
+  PF_CLK();   // diag 0
   for (int b = 0; b < nblk; b++) {
     const int b0 = b * DB;
-    if (warp == 0) diag_factor_invert(G + b0 * GLD + b0, Mi + b * DB * MLD, lane, b0, bad);
-    __syncthreads();
-    PF_CLK();   // diag
     const int r_first = b0 + DB;
     const int nstrips = (wp - r_first) / 8;
     // panel: rows below, P = S_ib * inv(L_bb)^T   (a warp owns whole 8-row strips -> in place)
@@ -342,25 +351,47 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
     }
     __syncthreads();
     PF_CLK();   // panel
-    // trailing update: S_ic -= P_i P_c^T for r_first <= c-tile <= row strip
-    for (int s = warp; s < nstrips; s += PF_WARPS) {
-      const int r0 = r_first + s * 8;
-      double af[KS];
-      const double* ap = G + (r0 + (lane >> 2)) * GLD + b0 + (lane & 3);
+    // trailing update S_ic -= P_i P_c^T for r_first <= c-tile <= row strip.  Strips 0 .. NT-1 only touch the next
+    // diagonal block: warp 0 takes them and goes on to factor that block; the other warps share the remaining strips.
+    if (warp == 0) {
+      for (int s = 0; s < NT && s < nstrips; s++) {
+        const int r0 = r_first + s * 8;
+        double af[KS];
+        const double* ap = G + (r0 + (lane >> 2)) * GLD + b0 + (lane & 3);
 #pragma unroll
-      for (int ks = 0; ks < KS; ks++) af[ks] = ap[ks * 4];
-      for (int c0 = r_first; c0 <= r0; c0 += 8) {
-        double acc[2] = {0.0, 0.0};
-        const double* bp = G + (c0 + (lane >> 2)) * GLD + b0 + (lane & 3);
+        for (int ks = 0; ks < KS; ks++) af[ks] = ap[ks * 4];
+        for (int c0 = r_first; c0 <= r0; c0 += 8) {
+          double acc[2] = {0.0, 0.0};
+          const double* bp = G + (c0 + (lane >> 2)) * GLD + b0 + (lane & 3);
 #pragma unroll
-        for (int ks = 0; ks < KS; ks++) dmma8x8x4(acc, af[ks], bp[ks * 4]);
-        double* cp = G + (r0 + (lane >> 2)) * GLD + c0 + (lane & 3) * 2;
-        cp[0] -= acc[0];
-        cp[1] -= acc[1];
+          for (int ks = 0; ks < KS; ks++) dmma8x8x4(acc, af[ks], bp[ks * 4]);
+          double* cp = G + (r0 + (lane >> 2)) * GLD + c0 + (lane & 3) * 2;
+          cp[0] -= acc[0];
+          cp[1] -= acc[1];
+        }
+      }
+      __syncwarp();
+      if (b + 1 < nblk) diag_factor_invert(G + r_first * GLD + r_first, Mi + (b + 1) * DB * MLD, lane, r_first, bad);
+    } else {
+      for (int s = NT + (warp - 1); s < nstrips; s += PF_WARPS - 1) {
+        const int r0 = r_first + s * 8;
+        double af[KS];
+        const double* ap = G + (r0 + (lane >> 2)) * GLD + b0 + (lane & 3);
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) af[ks] = ap[ks * 4];
+        for (int c0 = r_first; c0 <= r0; c0 += 8) {
+          double acc[2] = {0.0, 0.0};
+          const double* bp = G + (c0 + (lane >> 2)) * GLD + b0 + (lane & 3);
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) dmma8x8x4(acc, af[ks], bp[ks * 4]);
+          double* cp = G + (r0 + (lane >> 2)) * GLD + c0 + (lane & 3) * 2;
+          cp[0] -= acc[0];
+          cp[1] -= acc[1];
+        }
       }
     }
     __syncthreads();
-    PF_CLK();   // update
+    PF_CLK();   // update + next diag
   }
 
   // ---- inverse assembly: X_ik (i > k) is kept at block position (k, i) of G (upper triangle, untransposed)

@@ -28,6 +28,11 @@ struct TileCfg {
 };
 using TilePair = TileCfg<128, 64, 3, 2>;   // 3 x 30 KB (padded) = 90 KB -> two CTAs fit in 228 KB
 using TileBig = TileCfg<128, 128, 4, 1>;
+// Small problems (the TRSM / inner updates INSIDE a 512-wide diagonal block: <= 384 rows): with 128-row tiles they ran
+// on 3-12 CTAs and were bound by the FP64 rate of those few SMs (~17 us each, on the critical path of every panel).
+// Half-size tiles spread the same flops over 2-4x as many SMs.
+using TileSmall = TileCfg<64, 64, 3, 2>;        // 2 warps, updates C -= A B^T
+using TileSmallWide = TileCfg<64, 128, 3, 1>;   // 4 warps, in-place TRSM (a CTA owns whole rows of the <= 128-col panel)
 
 enum Act { ACT_RELU = 0, ACT_ERF = 1 };
 enum Arch { ARCH_MLP = 0, ARCH_RESNET = 1 };
