@@ -263,6 +263,20 @@ int smnngp_mg_timeline_read(smnngp_mg* g, int cap, int* panel_out, int* label_ou
 const char* smnngp_mg_last_error(void);
 int smnngp_lml_mg_f64(smnngp_mg* g, void* stream, const double* X, const double* y, int64_t D, int n_hidden, int act,
                       int arch, const double* hp_dev, int kind, int shift, double* out_dev, int* info_dev);
+/* NNGPKernel.predict (spax/kernels.py:29-32) / SPR.test_nll (spax/models.py:100-120, spax/likelihoods.py:30-33, :52-65)
+ * on the handle group.  smnngp_mg_create_predict: T test points and C right-hand sides ride through the distributed
+ * factorisation as extra global rows.  predict: Y [N, C] row-major, Xt [T, D] -> mean_out [T, C], var_out [T] (diag of
+ * the posterior covariance), identical on every rank; shift = SMNNGP_SHIFT_EPS_REL for the reference semantics.
+ * test_nll: g_pred built with c = 1, g_lik a plain smnngp_mg_create handle of the same n / block / group (second
+ * factorisation K + 1e-6 (a/b) I of the Student-t likelihood; may be NULL for kind = gauss) -> nll_out_dev [1]. */
+int smnngp_mg_create_predict(smnngp_mg** out, int rank, int world, int64_t n, int64_t t, int64_t c, int64_t block);
+int smnngp_predict_mg_f64(smnngp_mg* g, void* stream, const double* X, const double* Y, const double* Xt, int64_t D,
+                          int n_hidden, int act, int arch, const double* hp_dev, int shift, double* mean_out,
+                          double* var_out, int* info_dev);
+int smnngp_test_nll_mg_f64(smnngp_mg* g_pred, smnngp_mg* g_lik, void* stream, const double* X, const double* y,
+                           const double* Xt, const double* yt, int64_t D, int n_hidden, int act, int arch,
+                           const double* hp_dev, int kind, double y_mean, double y_std, double* nll_out_dev,
+                           double* mean_out, double* var_out, int* info_dev);
 
 /* ---- peer memory (multi-GPU, one process per GPU): cudaMalloc'ed buffers exported / imported as 64-byte CUDA IPC
  * handles so that every rank can store into every other rank's panel buffer over NVLink (no reference

@@ -41,6 +41,7 @@ EXPORTS = [
     "smnngp_mg_create", "smnngp_mg_destroy", "smnngp_mg_ipc_handle", "smnngp_mg_region", "smnngp_mg_connect_ipc",
     "smnngp_mg_connect_ptrs", "smnngp_mg_connect_emulated", "smnngp_mg_set_timeout", "smnngp_mg_set_sm_reserve",
     "smnngp_mg_timeline", "smnngp_mg_timeline_read", "smnngp_mg_last_error", "smnngp_lml_mg_f64",
+    "smnngp_mg_create_predict", "smnngp_predict_mg_f64", "smnngp_test_nll_mg_f64",
 ]
 
 
@@ -210,6 +211,10 @@ def _declare(lib):
     lib.smnngp_mg_timeline_read.argtypes = [_vp, _i, _vp, _vp, _vp]
     lib.smnngp_mg_last_error.restype = C.c_char_p
     lib.smnngp_lml_mg_f64.argtypes = [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _i, _vp, _vp]
+    lib.smnngp_mg_create_predict.argtypes = [_vp, _i, _i, _i64, _i64, _i64, _i64]
+    lib.smnngp_predict_mg_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp]
+    lib.smnngp_test_nll_mg_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _d, _d, _vp,
+                                           _vp, _vp, _vp]
     lib.smnngp_instr_reset.restype = None
     lib.smnngp_instr_reset.argtypes = [_i]
     lib.smnngp_instr_launches.restype = C.c_longlong

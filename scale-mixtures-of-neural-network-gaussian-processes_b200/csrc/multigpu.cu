@@ -36,8 +36,10 @@ using namespace smnngp;
 
 namespace {
 
-constexpr int FLAG_WORDS = 32;     // word 0: W ready; 8..15: panel ready (per source rank); 16..23: reduce slot ready
-constexpr int FLAG_W = 0, FLAG_PANEL = 8, FLAG_REDUCE = 16;
+// flag words: 0: W ready; 8..15: panel ready (per source rank); 16..23: reduce slot ready; 24..31: right-hand-side
+// rows (L^-1 Y)^T ready; 32..39: predictive results ready
+constexpr int FLAG_WORDS = 64;
+constexpr int FLAG_W = 0, FLAG_PANEL = 8, FLAG_REDUCE = 16, FLAG_Z = 24, FLAG_RES = 32;
 constexpr int REDUCE_DOUBLES = 4;  // per source rank: sum log L_ii, ||z||^2, info (as double), pad
 
 inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
@@ -49,17 +51,25 @@ struct TimelineMark { int panel, label; cudaEvent_t ev; };
 struct smnngp_mg {
   int rank = 0, P = 1, device = 0;
   long long n = 0, extra = 1, db = 512, ld = 0, mtotal = 0, nblocks = 0, mloc = 0;
+  // predictive handle: rows n .. n+c-1 = Y^T (right-hand sides), rows n+c .. n+c+t-1 = test-train cross-Gram;
+  // LML handle: t = 0, c = 1 (the single carried row y^T)
+  long long t = 0, c = 1;
+  long long extra_lo = 0, n_carried = 0;  // local storage keeps global order: the carried rows are its tail
   bool emulate = false, connected = false;
   std::atomic<bool> dead{false};
   // local storage
   double* a = nullptr;                    // [mloc, ld] block-row-cyclic rows
-  double *tab = nullptr, *q = nullptr, *scal = nullptr, *linv = nullptr, *zvec = nullptr, *sums = nullptr;
+  double *tab = nullptr, *q = nullptr, *scal = nullptr, *linv = nullptr, *carried = nullptr, *sums = nullptr;
+  double *tab_t = nullptr, *q_t = nullptr, *res_tmp = nullptr;      // predictive: test-point tables, local results
+  size_t tab_t_doubles = 0;
   double* ploc[2] = {nullptr, nullptr};   // solved panel rows in local order (A operand of the update)
   unsigned int* counters = nullptr;
+  int* info_tmp = nullptr;                // scratch status word (second factorisation of test_nll)
   size_t tab_doubles = 0;
-  // peer-visible region: [W db x db | flags | 3 panel slots n x db | reduce slots P x 4]
+  // peer-visible region: [W db x db | flags | 3 panel slots n x db | reduce slots P x 4 | Z c x n | results t x (c+1)]
   char* region = nullptr;
-  size_t off_w = 0, off_flags = 0, off_panel = 0, slot_bytes = 0, off_reduce = 0, region_bytes = 0;
+  size_t off_w = 0, off_flags = 0, off_panel = 0, slot_bytes = 0, off_reduce = 0, off_z = 0, off_res = 0,
+         region_bytes = 0;
   unsigned char handle[64] = {};
   char* bases[MAX_PEERS] = {};
   bool opened[MAX_PEERS] = {};
@@ -262,12 +272,13 @@ int panel_step(smnngp_mg* g, cudaStream_t s, long long p, int* info_dev, long lo
                                       g->rank, db, ls, c1, n, db, flag_ptrs, FLAG_PANEL + g->rank, seq,
                                       g->counters + 4));
   mark(g, s, (int)p, 2);                                                          // trsm
-  // z = L^-1 y: the carried row (global row n) sits at the end of its owner's storage
-  const long long bn = n / db;
-  if (m > 0 && g->rank == g->owner(bn)) {
-    const long long lrow = g->local_offset(bn) + (n - bn * db);
-    if (lrow >= ls)
-      MG_CU(cudaMemcpyAsync(g->zvec + c0, ploc + (lrow - ls) * db, (size_t)w * 8, cudaMemcpyDeviceToDevice, s));
+  // carried rows (global index >= n: y^T / Y^T rows, test-train cross-Gram rows) are the tail of the local storage:
+  // their solved panel columns only exist in ploc - keep them
+  {
+    const long long k = g->extra_lo - ls;                      // first carried row inside this rank's panel rows
+    if (m > k && k >= 0)
+      MG_CU(cudaMemcpy2DAsync(g->carried + c0, (size_t)g->ld * 8, ploc + k * db, (size_t)db * 8, (size_t)w * 8,
+                              (size_t)(m - k), cudaMemcpyDeviceToDevice, s));
   }
   if (c1 >= n) return SMNNGP_OK;
   if (g->emulate) MG_RC(smnngp_stage_wait_flags_f64(s, g->flags_local(), FLAG_PANEL + g->rank, 1, seq, g->timeout_s, info_dev));
@@ -276,8 +287,8 @@ int panel_step(smnngp_mg* g, cudaStream_t s, long long p, int* info_dev, long lo
   return SMNNGP_OK;
 }
 
-int build_gram(smnngp_mg* g, cudaStream_t s, const double* X, const double* y, long long D, int nh, int act, int arch,
-               const double* hp, int shift) {
+int build_gram(smnngp_mg* g, cudaStream_t s, const double* X, const double* y, const double* xt, long long D, int nh,
+               int act, int arch, const double* hp, int shift) {
   const long long n = g->n, db = g->db;
   const int n_act = std::max(n_act_applications(nh, arch), 1);
   if ((size_t)n_act * n > g->tab_doubles) {
@@ -287,6 +298,15 @@ int build_gram(smnngp_mg* g, cudaStream_t s, const double* X, const double* y, l
     g->tab_doubles = (size_t)n_act * n;
   }
   MG_RC(smnngp_stage_qtable_f64(s, X, n, D, nh, act, arch, hp, g->tab, n, g->q, g->scal));
+  if (xt != nullptr && g->t > 0) {
+    if ((size_t)n_act * g->t > g->tab_t_doubles) {
+      if (g->tab_t) cudaFree(g->tab_t);
+      g->tab_t = nullptr;
+      MG_CU(cudaMalloc(&g->tab_t, (size_t)n_act * g->t * 8));
+      g->tab_t_doubles = (size_t)n_act * g->t;
+    }
+    MG_RC(smnngp_stage_qtable_f64(s, xt, g->t, D, nh, act, arch, hp, g->tab_t, g->t, g->q_t, nullptr));
+  }
   for (long long b = g->rank; b < g->nblocks; b += g->P) {
     const long long g0 = b * db, lo = g->local_offset(b);
     const long long rows = std::min(g0 + g->block_rows(b), n) - g0;          // rows of the square part in this block
@@ -299,8 +319,20 @@ int build_gram(smnngp_mg* g, cudaStream_t s, const double* X, const double* y, l
       MG_RC(smnngp_stage_gram_f64(s, xb, rows, xb, rows, D, nh, act, arch, hp, g->tab + g0, n, g->tab + g0, n, g->scal,
                                   shift, 1, arow + g0, g->ld));
     }
-    if (g0 <= n && n < g0 + g->block_rows(b))                              // the appended row y^T
-      MG_CU(cudaMemcpyAsync(g->a + (lo + (n - g0)) * g->ld, y, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    const long long g1 = g0 + g->block_rows(b);
+    if (g1 > n) {                                                          // this block holds carried rows
+      // right-hand sides: global rows n .. n+c-1 = the columns of Y [N, C] (LML: the single row y^T)
+      for (long long j = std::max(g0, n); j < std::min(g1, n + g->c); j++) {
+        double* dst = g->a + (lo + (j - g0)) * g->ld;
+        if (g->c == 1) MG_CU(cudaMemcpyAsync(dst, y, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+        else MG_CU(cudaMemcpy2DAsync(dst, 8, y + (j - n), (size_t)g->c * 8, 8, (size_t)n, cudaMemcpyDeviceToDevice, s));
+      }
+      // test points held by this block: rows of the test-train cross-Gram
+      const long long t0 = std::max(g0, n + g->c) - (n + g->c), t1 = g1 - (n + g->c);
+      if (xt != nullptr && t1 > t0)
+        MG_RC(smnngp_stage_gram_f64(s, xt + t0 * D, t1 - t0, X, n, D, nh, act, arch, hp, g->tab_t + t0, g->t, g->tab, n,
+                                    g->scal, SHIFT_NONE, 0, g->a + (lo + (n + g->c + t0 - g0)) * g->ld, g->ld));
+    }
   }
   return SMNNGP_OK;
 }
@@ -311,41 +343,54 @@ extern "C" {
 
 const char* smnngp_mg_last_error(void) { return g_mg_err; }
 
-int smnngp_mg_create(smnngp_mg** out, int rank, int world, int64_t n, int64_t block) {
+static int mg_create_impl(smnngp_mg** out, int rank, int world, int64_t n, int64_t block, int64_t t, int64_t c) {
   if (!out || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || n <= 0 || block <= 0 || block % PB != 0 ||
-      block > LINV_BLOCKS * PB || n + 1 > INT32_MAX)
+      block > LINV_BLOCKS * PB || t < 0 || c < 1 || n + t + c > INT32_MAX)
     return mg_fail(SMNNGP_EINVAL, "smnngp_mg_create: invalid argument");
   smnngp_mg* g = new smnngp_mg();
-  g->rank = rank; g->P = world; g->n = n; g->db = block;
+  g->rank = rank; g->P = world; g->n = n; g->db = block; g->t = t; g->c = c;
+  g->extra = t + c;
   cudaGetDevice(&g->device);
   g->mtotal = n + g->extra;
   g->nblocks = cdiv(g->mtotal, g->db);
   g->ld = cdiv(n, 16) * 16;
   g->mloc = g->local_rows(rank);
+  for (long long b = rank; b < g->nblocks; b += world) {      // local rows with global index < n
+    const long long g0 = b * g->db, g1 = g0 + g->block_rows(b);
+    g->extra_lo += std::max<long long>(0, std::min<long long>(g1, n) - g0);
+  }
+  g->n_carried = g->mloc - g->extra_lo;
   g->off_w = 0;
   g->off_flags = (size_t)g->db * g->db * 8;
   g->off_panel = g->off_flags + FLAG_WORDS * 8;
   g->slot_bytes = (size_t)n * g->db * 8;
   g->off_reduce = g->off_panel + 3 * g->slot_bytes;
-  g->region_bytes = g->off_reduce + (size_t)MAX_PEERS * REDUCE_DOUBLES * 8;
+  g->off_z = g->off_reduce + (size_t)MAX_PEERS * REDUCE_DOUBLES * 8;
+  g->off_res = g->off_z + (t > 0 ? (size_t)c * n * 8 : 0);
+  g->region_bytes = g->off_res + (t > 0 ? (size_t)t * (c + 1) * 8 : 0) + 256;
   void* reg = nullptr;
   if (smnngp_peer_alloc(g->region_bytes, &reg, g->handle) != SMNNGP_OK) {
     delete g;
     return mg_fail(SMNNGP_ECUDA, "smnngp_mg_create: peer region allocation / IPC export failed");
   }
   g->region = static_cast<char*>(reg);
-  const long long mrows = std::max<long long>(g->mloc, 1);
+  const long long mrows = std::max<long long>(g->mloc, 1), crow = std::max<long long>(g->n_carried, 1);
   bool ok = cudaMemset(g->region + g->off_flags, 0, FLAG_WORDS * 8) == cudaSuccess &&
             cudaMemset(g->region + g->off_reduce, 0, MAX_PEERS * REDUCE_DOUBLES * 8) == cudaSuccess &&
             cudaMalloc(&g->a, (size_t)mrows * g->ld * 8) == cudaSuccess &&
             cudaMalloc(&g->q, (size_t)n * 8) == cudaSuccess && cudaMalloc(&g->scal, SC_COUNT * 8) == cudaSuccess &&
             cudaMalloc(&g->linv, (size_t)LINV_BLOCKS * PB * PB * 8) == cudaSuccess &&
-            cudaMalloc(&g->zvec, (size_t)n * 8) == cudaSuccess && cudaMalloc(&g->sums, 2 * 8) == cudaSuccess &&
+            cudaMalloc(&g->carried, (size_t)crow * g->ld * 8) == cudaSuccess &&
+            cudaMalloc(&g->sums, 2 * 8) == cudaSuccess &&
             cudaMalloc(&g->ploc[0], (size_t)mrows * g->db * 8) == cudaSuccess &&
             cudaMalloc(&g->ploc[1], (size_t)mrows * g->db * 8) == cudaSuccess &&
             cudaMalloc(&g->counters, 8 * sizeof(unsigned int)) == cudaSuccess &&
+            cudaMalloc(&g->info_tmp, sizeof(int)) == cudaSuccess &&
             cudaMemset(g->counters, 0, 8 * sizeof(unsigned int)) == cudaSuccess &&
-            cudaMemset(g->zvec, 0, (size_t)n * 8) == cudaSuccess;
+            cudaMemset(g->carried, 0, (size_t)crow * g->ld * 8) == cudaSuccess;
+  if (ok && t > 0)
+    ok = cudaMalloc(&g->q_t, (size_t)t * 8) == cudaSuccess &&
+         cudaMalloc(&g->res_tmp, (size_t)t * (c + 1) * 8) == cudaSuccess;
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
   ok = ok && cudaStreamCreateWithPriority(&g->side, cudaStreamNonBlocking, hi) == cudaSuccess &&
@@ -363,6 +408,16 @@ int smnngp_mg_create(smnngp_mg** out, int rank, int world, int64_t n, int64_t bl
   g->dog = std::thread(watchdog_main, g);
   *out = g;
   return SMNNGP_OK;
+}
+
+int smnngp_mg_create(smnngp_mg** out, int rank, int world, int64_t n, int64_t block) {
+  return mg_create_impl(out, rank, world, n, block, 0, 1);
+}
+// handle for smnngp_predict_mg_f64 / smnngp_test_nll_mg_f64: T test points and C right-hand sides ride along as extra
+// global rows of the same layout
+int smnngp_mg_create_predict(smnngp_mg** out, int rank, int world, int64_t n, int64_t t, int64_t c, int64_t block) {
+  if (t <= 0) return mg_fail(SMNNGP_EINVAL, "smnngp_mg_create_predict: t must be positive");
+  return mg_create_impl(out, rank, world, n, block, t, c);
 }
 
 int smnngp_mg_ipc_handle(smnngp_mg* g, unsigned char* handle_out64) {
@@ -468,9 +523,11 @@ int smnngp_mg_destroy(smnngp_mg* g) {
   for (int r = 0; r < MAX_PEERS; r++)
     if (g->opened[r]) smnngp_peer_close(g->bases[r]);
   if (g->region) smnngp_peer_free(g->region);
-  for (double* p : {g->a, g->tab, g->q, g->scal, g->linv, g->zvec, g->sums, g->ploc[0], g->ploc[1]})
+  for (double* p : {g->a, g->tab, g->q, g->scal, g->linv, g->carried, g->sums, g->ploc[0], g->ploc[1], g->tab_t, g->q_t,
+                    g->res_tmp})
     if (p) cudaFree(p);
   if (g->counters) cudaFree(g->counters);
+  if (g->info_tmp) cudaFree(g->info_tmp);
   for (cudaEvent_t e : {g->ev_panel, g->ev_a, g->ev_fork, g->ev_done})
     if (e) cudaEventDestroy(e);
   if (g->side) cudaStreamDestroy(g->side);
@@ -480,28 +537,20 @@ int smnngp_mg_destroy(smnngp_mg* g) {
   return SMNNGP_OK;
 }
 
-// SPR.loss (spax/models.py:93-98) on the ranks that share the handle group: out_dev[4] = {log p(y), -log p(y) / N,
-// sum log L_ii, ||L^-1 y||^2}, identical on every rank.  Every rank calls with the SAME X [N, D], y [N], hp_dev [6]
-// (device pointers on ITS device).  shift: SMNNGP_SHIFT_* added to the Gram diagonal (SHIFT_EPS_ABS for SPR.loss).
-int smnngp_lml_mg_f64(smnngp_mg* g, void* stream, const double* X, const double* y, int64_t D, int n_hidden, int act,
-                      int arch, const double* hp_dev, int kind, int shift, double* out_dev, int* info_dev) {
-  if (!g || !X || !y || !hp_dev || !out_dev || !info_dev || D <= 0 || n_hidden < 0 || n_hidden > 64 ||
-      (act != ACT_RELU && act != ACT_ERF) || (arch != ARCH_MLP && arch != ARCH_RESNET) ||
-      (kind != KIND_GAUSS && kind != KIND_STUDENT_T) || shift < 0 || shift > 3)
-    return mg_fail(SMNNGP_EINVAL, "smnngp_lml_mg_f64: invalid argument");
-  if (!g->connected) return mg_fail(SMNNGP_EINVAL, "smnngp_lml_mg_f64: handle not connected to its peers");
-  if (g->dead) return mg_fail(SMNNGP_ECUDA, "smnngp_lml_mg_f64: handle was poisoned by a peer time-out");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  Enter scope(s);
-  if (scope.dev != g->device) return mg_fail(SMNNGP_EINVAL, "smnngp_lml_mg_f64: stream belongs to another device");
+}  // extern "C" (helpers below are internal)
+
+namespace {
+
+// Gram rows of this rank + right-looking factorisation with one panel of look-ahead (see file comment)
+int factor_all(smnngp_mg* g, cudaStream_t s, const double* X, const double* y, const double* xt, long long D, int nh,
+               int act, int arch, const double* hp_dev, int shift, int* info_dev) {
   const long long n = g->n, db = g->db;
   const int P = g->P;
   mark(g, s, -1, 7);                                                 // start (Gram stage follows)
   MG_CU(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
   MG_CU(cudaMemsetAsync(g->sums, 0, 2 * sizeof(double), s));
-  MG_RC(build_gram(g, s, X, y, D, n_hidden, act, arch, hp_dev, shift));
+  MG_RC(build_gram(g, s, X, y, xt, D, nh, act, arch, hp_dev, shift));
   const long long npanels = cdiv(n, db);
-  // ---- right-looking factorisation with one panel of look-ahead ----
   MG_CU(cudaEventRecord(g->ev_fork, s));
   MG_CU(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
   long long ls = 0, m = 0;
@@ -540,41 +589,232 @@ int smnngp_lml_mg_f64(smnngp_mg* g, void* stream, const double* X, const double*
     ls = ls2;
     m = m2;
   }
-  // ---- ||L^-1 y||^2 on the owner of the carried row, then the cross-rank reduction through the peer slots ----
-  const long long bn = n / db;
-  if (g->rank == g->owner(bn)) MG_CU(launch_sumsq(s, g->zvec, n, g->sums + 1));
-  {
-    void* red_ptrs[MAX_PEERS];
-    void* flag_ptrs[MAX_PEERS];
-    fill_ptrs(g, g->off_reduce, red_ptrs);
-    fill_ptrs(g, g->off_flags, flag_ptrs);
-    const unsigned long long seq = g->seq_base + (unsigned long long)npanels + 1;
-    PeerSignal sg{};
-    sg.P = P; sg.seq = seq; sg.counter = nullptr;
-    for (int r = 0; r < MAX_PEERS; r++) {
-      const bool on = flag_ptrs[r] != nullptr && (!g->emulate || r == g->rank);
-      sg.flag[r] = on ? static_cast<unsigned long long*>(flag_ptrs[r]) + FLAG_REDUCE + g->rank : nullptr;
-      if (!on) red_ptrs[r] = nullptr;
-    }
-    reduce_scatter_kernel<<<1, 1, 0, s>>>(g->sums, info_dev, g->rank, (double*)red_ptrs[0], (double*)red_ptrs[1],
-                                          (double*)red_ptrs[2], (double*)red_ptrs[3], (double*)red_ptrs[4],
-                                          (double*)red_ptrs[5], (double*)red_ptrs[6], (double*)red_ptrs[7], sg);
-    instr().launches++;
-    MG_CU(cudaGetLastError());
-    if (g->emulate) {
-      MG_RC(smnngp_stage_wait_flags_f64(s, g->flags_local(), FLAG_REDUCE + g->rank, 1, seq, g->timeout_s, info_dev));
-    } else {
-      MG_RC(smnngp_stage_wait_flags_f64(s, g->flags_local(), FLAG_REDUCE, P, seq, g->timeout_s, info_dev));
-    }
-    const double* slots = reinterpret_cast<const double*>(g->region + g->off_reduce);
-    if (g->emulate) reduce_gather_kernel<<<1, 1, 0, s>>>(slots + g->rank * REDUCE_DOUBLES, 1, g->scal, info_dev);
-    else reduce_gather_kernel<<<1, 1, 0, s>>>(slots, P, g->scal, info_dev);
-    instr().launches++;
-    MG_CU(cudaGetLastError());
+  return SMNNGP_OK;
+}
+
+void signal_for(smnngp_mg* g, int word, unsigned long long seq, PeerSignal& sg, void** data_ptrs, size_t data_off) {
+  void* flag_ptrs[MAX_PEERS];
+  fill_ptrs(g, g->off_flags, flag_ptrs);
+  if (data_ptrs) fill_ptrs(g, data_off, data_ptrs);
+  sg = PeerSignal{};
+  sg.P = g->P; sg.seq = seq; sg.counter = nullptr;
+  for (int r = 0; r < MAX_PEERS; r++) {
+    const bool on = flag_ptrs[r] != nullptr && (!g->emulate || r == g->rank);
+    sg.flag[r] = on ? static_cast<unsigned long long*>(flag_ptrs[r]) + word + g->rank : nullptr;
+    if (!on && data_ptrs) data_ptrs[r] = nullptr;
   }
+}
+
+int wait_all(smnngp_mg* g, cudaStream_t s, int word, unsigned long long seq, int* info_dev) {
+  if (g->emulate) return smnngp_stage_wait_flags_f64(s, g->flags_local(), word + g->rank, 1, seq, g->timeout_s, info_dev);
+  return smnngp_stage_wait_flags_f64(s, g->flags_local(), word, g->P, seq, g->timeout_s, info_dev);
+}
+
+// {sum log L_ii, ||z||^2, info} of every rank -> scal[SC_LOGDET], scal[SC_QUAD], info (max), same on every rank
+int reduce_all(smnngp_mg* g, cudaStream_t s, unsigned long long seq, int* info_dev) {
+  void* red_ptrs[MAX_PEERS];
+  PeerSignal sg;
+  signal_for(g, FLAG_REDUCE, seq, sg, red_ptrs, g->off_reduce);
+  reduce_scatter_kernel<<<1, 1, 0, s>>>(g->sums, info_dev, g->rank, (double*)red_ptrs[0], (double*)red_ptrs[1],
+                                        (double*)red_ptrs[2], (double*)red_ptrs[3], (double*)red_ptrs[4],
+                                        (double*)red_ptrs[5], (double*)red_ptrs[6], (double*)red_ptrs[7], sg);
+  instr().launches++;
+  MG_CU(cudaGetLastError());
+  MG_RC(wait_all(g, s, FLAG_REDUCE, seq, info_dev));
+  const double* slots = reinterpret_cast<const double*>(g->region + g->off_reduce);
+  if (g->emulate) reduce_gather_kernel<<<1, 1, 0, s>>>(slots + g->rank * REDUCE_DOUBLES, 1, g->scal, info_dev);
+  else reduce_gather_kernel<<<1, 1, 0, s>>>(slots, g->P, g->scal, info_dev);
+  instr().launches++;
+  MG_CU(cudaGetLastError());
+  return SMNNGP_OK;
+}
+
+// rows [rows x width] (pitch lds) -> the same offset of every rank's buffer (pitch ldd); optional flag afterwards
+struct PeerCopy {
+  const double* src;
+  long long lds, ldd, rows, width;
+  double* dst[MAX_PEERS];
+  int P;
+};
+__global__ void peer_copy_kernel(const PeerCopy pc) {
+  const long long total = pc.rows * pc.width;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / pc.width, c = e - r * pc.width;
+    const double v = pc.src[r * pc.lds + c];
+#pragma unroll
+    for (int q = 0; q < MAX_PEERS; q++)
+      if (q < pc.P && pc.dst[q] != nullptr) pc.dst[q][r * pc.ldd + c] = v;
+  }
+}
+__global__ void fold_info_kernel(const int* __restrict__ src, int* __restrict__ dst) {
+  if (*src != 0) atomicMax(dst, *src);
+}
+__global__ void flag_kernel(PeerSignal sg) {
+  __threadfence_system();
+  for (int q = 0; q < sg.P; q++)
+    if (sg.flag[q] != nullptr) st_release_sys(sg.flag[q], sg.seq);
+}
+
+int check_call(smnngp_mg* g, cudaStream_t s, const Enter& scope, const char* who) {
+  if (!g->connected) return mg_fail(SMNNGP_EINVAL, "handle not connected to its peers");
+  if (g->dead) return mg_fail(SMNNGP_ECUDA, "handle was poisoned by a peer time-out");
+  if (scope.dev != g->device) return mg_fail(SMNNGP_EINVAL, "stream belongs to another device than the handle");
+  (void)s; (void)who;
+  return SMNNGP_OK;
+}
+
+bool valid_stack_mg(int n_hidden, int act, int arch) {
+  return n_hidden >= 0 && n_hidden <= 64 && (act == ACT_RELU || act == ACT_ERF) && (arch == ARCH_MLP || arch == ARCH_RESNET);
+}
+
+}  // namespace
+
+extern "C" {
+
+// SPR.loss (spax/models.py:93-98) on the ranks that share the handle group: out_dev[4] = {log p(y), -log p(y) / N,
+// sum log L_ii, ||L^-1 y||^2}, identical on every rank.  Every rank calls with the SAME X [N, D], y [N], hp_dev [6]
+// (device pointers on ITS device).  shift: SMNNGP_SHIFT_* added to the Gram diagonal (SHIFT_EPS_ABS for SPR.loss).
+int smnngp_lml_mg_f64(smnngp_mg* g, void* stream, const double* X, const double* y, int64_t D, int n_hidden, int act,
+                      int arch, const double* hp_dev, int kind, int shift, double* out_dev, int* info_dev) {
+  if (!g || !X || !y || !hp_dev || !out_dev || !info_dev || D <= 0 || !valid_stack_mg(n_hidden, act, arch) ||
+      (kind != KIND_GAUSS && kind != KIND_STUDENT_T) || shift < 0 || shift > 3 || g->t != 0 || g->c != 1)
+    return mg_fail(SMNNGP_EINVAL, "smnngp_lml_mg_f64: invalid argument (needs a handle from smnngp_mg_create)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
+  MG_RC(check_call(g, s, scope, "smnngp_lml_mg_f64"));
+  const long long n = g->n, npanels = cdiv(n, g->db);
+  MG_RC(factor_all(g, s, X, y, nullptr, D, n_hidden, act, arch, hp_dev, shift, info_dev));
+  // ||L^-1 y||^2 on the owner of the carried row, then the cross-rank reduction through the peer slots
+  if (g->n_carried > 0) MG_CU(launch_sumsq(s, g->carried, n, g->sums + 1));
+  MG_RC(reduce_all(g, s, g->seq_base + (unsigned long long)npanels + 1, info_dev));
   MG_CU(launch_lml_finalize(s, g->scal, hp_dev, kind, n, info_dev, out_dev));
-  g->seq_base += (unsigned long long)npanels + 2;
+  g->seq_base += (unsigned long long)npanels + 4;
   arm_watchdog(g, s, info_dev);
+  return SMNNGP_OK;
+}
+
+// NNGPKernel.predict (spax/kernels.py:29-32; neural_tangents gradient_descent_mse_ensemble) on the ranks of the handle
+// group: mean_out [T, C], var_out [T] (= diag of the posterior covariance), identical on every rank.  Y [N, C]
+// row-major, Xt [T, D].  The C right-hand sides and the T test-train cross-Gram rows ride through the distributed
+// factorisation as extra global rows (never exchanged); (L^-1 Y)^T is then stored to every rank, every rank finishes
+// ITS test points and stores the results to every rank.  shift = SMNNGP_SHIFT_EPS_REL for the reference semantics.
+int smnngp_predict_mg_f64(smnngp_mg* g, void* stream, const double* X, const double* Y, const double* Xt, int64_t D,
+                          int n_hidden, int act, int arch, const double* hp_dev, int shift, double* mean_out,
+                          double* var_out, int* info_dev) {
+  if (!g || !X || !Y || !Xt || !hp_dev || !mean_out || !var_out || !info_dev || D <= 0 ||
+      !valid_stack_mg(n_hidden, act, arch) || shift < 0 || shift > 3 || g->t <= 0)
+    return mg_fail(SMNNGP_EINVAL, "smnngp_predict_mg_f64: invalid argument (needs a handle from smnngp_mg_create_predict)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
+  MG_RC(check_call(g, s, scope, "smnngp_predict_mg_f64"));
+  const long long n = g->n, db = g->db, T = g->t, C = g->c, npanels = cdiv(n, db);
+  const unsigned long long seq0 = g->seq_base + (unsigned long long)npanels;
+  MG_RC(factor_all(g, s, X, Y, Xt, D, n_hidden, act, arch, hp_dev, shift, info_dev));
+  MG_RC(reduce_all(g, s, seq0 + 1, info_dev));                      // info of every rank (a non-PD block anywhere)
+  double* zloc = reinterpret_cast<double*>(g->region + g->off_z);
+  double* rloc = reinterpret_cast<double*>(g->region + g->off_res);  // [T, C] means then [T] variances
+  // (1) right-hand-side rows (L^-1 Y)^T this rank carried -> every rank's Z [C, n]
+  {
+    void* zp[MAX_PEERS];
+    PeerSignal sg;
+    signal_for(g, FLAG_Z, seq0 + 2, sg, zp, g->off_z);
+    long long row = 0;                                               // index into the carried rows (global order)
+    for (long long b = g->rank; b < g->nblocks; b += g->P) {
+      const long long g0 = b * db, g1 = g0 + g->block_rows(b);
+      if (g1 <= n) continue;
+      const long long j0 = std::max(g0, n), j1 = std::min(g1, n + C);   // right-hand sides in this block
+      if (j1 > j0) {
+        PeerCopy pc{};
+        pc.src = g->carried + row * g->ld; pc.lds = g->ld; pc.ldd = n; pc.rows = j1 - j0; pc.width = n; pc.P = g->P;
+        for (int r = 0; r < MAX_PEERS; r++) pc.dst[r] = zp[r] ? static_cast<double*>(zp[r]) + (j0 - n) * n : nullptr;
+        peer_copy_kernel<<<148, 256, 0, s>>>(pc);
+        instr().launches++;
+        MG_CU(cudaGetLastError());
+      }
+      row += g1 - std::max(g0, n);
+    }
+    flag_kernel<<<1, 1, 0, s>>>(sg);
+    instr().launches++;
+    MG_CU(cudaGetLastError());
+    MG_RC(wait_all(g, s, FLAG_Z, seq0 + 2, info_dev));
+  }
+  // (2) predictive moments of this rank's test points -> every rank's result buffer
+  {
+    void* rp[MAX_PEERS];
+    PeerSignal sg;
+    signal_for(g, FLAG_RES, seq0 + 3, sg, rp, g->off_res);
+    long long row = 0;
+    for (long long b = g->rank; b < g->nblocks; b += g->P) {
+      const long long g0 = b * db, g1 = g0 + g->block_rows(b);
+      if (g1 <= n) continue;
+      const long long first = std::max(g0, n);
+      const long long t0 = std::max(g0, n + C) - (n + C), t1 = g1 - (n + C);
+      if (t1 > t0) {
+        const double* V = g->carried + (row + (n + C + t0 - first)) * g->ld;
+        double* mean_l = g->res_tmp + t0 * C;
+        double* var_l = g->res_tmp + T * C + t0;
+        MG_CU(launch_predict_finalize(s, V, g->ld, zloc, n, g->q_t + t0, (int)(t1 - t0), (int)C, n, info_dev, mean_l,
+                                      var_l));
+        PeerCopy pm{};
+        pm.src = mean_l; pm.lds = C; pm.ldd = C; pm.rows = t1 - t0; pm.width = C; pm.P = g->P;
+        PeerCopy pv{};
+        pv.src = var_l; pv.lds = t1 - t0; pv.ldd = t1 - t0; pv.rows = 1; pv.width = t1 - t0; pv.P = g->P;
+        for (int r = 0; r < MAX_PEERS; r++) {
+          pm.dst[r] = rp[r] ? static_cast<double*>(rp[r]) + t0 * C : nullptr;
+          pv.dst[r] = rp[r] ? static_cast<double*>(rp[r]) + T * C + t0 : nullptr;
+        }
+        peer_copy_kernel<<<64, 256, 0, s>>>(pm);
+        peer_copy_kernel<<<16, 256, 0, s>>>(pv);
+        instr().launches += 2;
+        MG_CU(cudaGetLastError());
+      }
+      row += g1 - first;
+    }
+    flag_kernel<<<1, 1, 0, s>>>(sg);
+    instr().launches++;
+    MG_CU(cudaGetLastError());
+    MG_RC(wait_all(g, s, FLAG_RES, seq0 + 3, info_dev));
+  }
+  MG_CU(cudaMemcpyAsync(mean_out, rloc, (size_t)T * C * 8, cudaMemcpyDeviceToDevice, s));
+  MG_CU(cudaMemcpyAsync(var_out, rloc + T * C, (size_t)T * 8, cudaMemcpyDeviceToDevice, s));
+  g->seq_base += (unsigned long long)npanels + 4;
+  arm_watchdog(g, s, info_dev);
+  return SMNNGP_OK;
+}
+
+// SPR.test_nll (spax/models.py:100-120) on the handle group: g_pred from smnngp_mg_create_predict(..., t, c = 1, ...),
+// g_lik from smnngp_mg_create (same n / block / group).  (1) predictive with the relative regulariser, (2) for the
+// Student-t likelihood the scale d = 2a + y^T ((b/a) K + 1e-6 I)^-1 y (spax/likelihoods.py:60-61) from a second
+// distributed factorisation of K + 1e-6 (a/b) I, (3) the closed-form tail.  nll_out_dev [1], mean_out [T], var_out [T].
+int smnngp_test_nll_mg_f64(smnngp_mg* g_pred, smnngp_mg* g_lik, void* stream, const double* X, const double* y,
+                           const double* Xt, const double* yt, int64_t D, int n_hidden, int act, int arch,
+                           const double* hp_dev, int kind, double y_mean, double y_std, double* nll_out_dev,
+                           double* mean_out, double* var_out, int* info_dev) {
+  if (!g_pred || !X || !y || !Xt || !yt || !hp_dev || !nll_out_dev || !mean_out || !var_out || !info_dev || g_pred->c != 1 || (kind != KIND_GAUSS && kind != KIND_STUDENT_T) ||
+      (kind == KIND_STUDENT_T && (!g_lik || g_lik->n != g_pred->n)))
+    return mg_fail(SMNNGP_EINVAL, "smnngp_test_nll_mg_f64: invalid argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MG_RC(smnngp_predict_mg_f64(g_pred, stream, X, y, Xt, D, n_hidden, act, arch, hp_dev, SMNNGP_SHIFT_EPS_REL, mean_out,
+                              var_out, info_dev));
+  const double* quad2 = mean_out;                                   // unused for the Gaussian likelihood
+  if (kind == KIND_STUDENT_T) {
+    // second factorisation: K + 1e-6 (a/b) I, ||L2^-1 y||^2 ends up in g_lik's scalar block.  It gets its own status
+    // word (factor_all clears the word it is given), folded into info_dev afterwards.
+    Enter scope(s);
+    MG_RC(check_call(g_lik, s, scope, "smnngp_test_nll_mg_f64"));
+    const long long n = g_lik->n, npanels = cdiv(n, g_lik->db);
+    MG_RC(factor_all(g_lik, s, X, y, nullptr, D, n_hidden, act, arch, hp_dev, SMNNGP_SHIFT_LIK, g_lik->info_tmp));
+    if (g_lik->n_carried > 0) MG_CU(launch_sumsq(s, g_lik->carried, n, g_lik->sums + 1));
+    MG_RC(reduce_all(g_lik, s, g_lik->seq_base + (unsigned long long)npanels + 1, g_lik->info_tmp));
+    fold_info_kernel<<<1, 1, 0, s>>>(g_lik->info_tmp, info_dev);
+    instr().launches++;
+    MG_CU(cudaGetLastError());
+    g_lik->seq_base += (unsigned long long)npanels + 4;
+    arm_watchdog(g_lik, s, info_dev);
+    quad2 = g_lik->scal + SC_QUAD;
+  }
+  MG_CU(launch_test_nll_finalize(s, mean_out, var_out, yt, (int)g_pred->t, g_pred->n, y_mean, y_std, hp_dev, kind, quad2,
+                                 info_dev, nullptr, nll_out_dev));
   return SMNNGP_OK;
 }
 

@@ -320,8 +320,7 @@ class DistributedLML:
         # exchange == "peer": the whole evaluation is ONE C call per rank (csrc/multigpu.cu, smnngp_lml_mg_f64); the
         # Python panel loop below remains for the NCCL exchange, the NumPy backend of the CPU suite, the predictive
         # driver (DistributedPredict) and as a cross-check (SMNNGP_MG_DRIVER=python)
-        use_c = (exchange == "peer" and type(self) is DistributedLML and
-                 os.environ.get("SMNNGP_MG_DRIVER", "c") == "c")
+        use_c = exchange == "peer" and os.environ.get("SMNNGP_MG_DRIVER", "c") == "c"
         if use_c:
             try:
                 self._create_mg(group)
@@ -365,7 +364,11 @@ class DistributedLML:
         lib, dev = self.be.lib, self.a.device
         h = C.c_void_p()
         with torch.cuda.device(dev):
-            ok = lib.smnngp_mg_create(C.byref(h), self.rank, self.world, self.n, self.db) == 0
+            tc = getattr(self, "_tc", None)          # DistributedPredict: (test points, right-hand sides)
+            if tc is None:
+                ok = lib.smnngp_mg_create(C.byref(h), self.rank, self.world, self.n, self.db) == 0
+            else:
+                ok = lib.smnngp_mg_create_predict(C.byref(h), self.rank, self.world, self.n, tc[0], tc[1], self.db) == 0
             handle = (C.c_ubyte * 64)()
             if ok:
                 lib.smnngp_mg_ipc_handle(h, handle)
@@ -410,6 +413,9 @@ class DistributedLML:
 
     def close(self):
         """release the peer-visible buffers (CUDA IPC mappings + the local cudaMalloc region)"""
+        if getattr(self, "_lik", None) is not None:
+            self._lik.close()
+            self._lik = None
         if self.mg is not None:
             with torch.cuda.device(self.a.device):
                 torch.cuda.synchronize(self.a.device)
@@ -701,9 +707,13 @@ class DistributedPredict(DistributedLML):
     tail is the single-GPU kernel on local rows."""
 
     def __init__(self, n, d, t, c, spec: StackSpec, device, **kw):
+        self._tc = (int(t), int(c))
         super().__init__(n, d, spec, device, extra_rows=int(c) + int(t), **kw)
         self.t, self.c = int(t), int(c)
         self.gram_shift = "eps_rel"
+        self._lik = None
+        if self.mg is not None:                   # C driver (smnngp_predict_mg_f64): nothing else to set up
+            return
         lay = self.lay
         g = [torch.arange(b * self.db, b * self.db + lay.block_rows(b)) for b in lay.local_blocks()]
         g = torch.cat(g) if g else torch.zeros(0, dtype=torch.int64)
@@ -738,6 +748,18 @@ class DistributedPredict(DistributedLML):
     def predict(self, x, y, x_test, hp):
         """(mean [T, C], var [T] = diag of the posterior covariance, info) - identical on every rank."""
         be, n, c, t, P = self.be, self.n, self.c, self.t, self.world
+        if self.mg is not None:                                    # one C call per rank (csrc/multigpu.cu)
+            nh, act, arch = self.spec.ids()
+            y2 = (y if y.ndim == 2 else y[:, None]).contiguous()
+            x, x_test = x.contiguous(), x_test.contiguous()
+            mean, var = be.empty(t, c), be.empty(t)
+            info = be.zeros(1, dtype=torch.int32)
+            rc = be.lib.smnngp_predict_mg_f64(self.mg, be._s(), be._p(x), be._p(y2), be._p(x_test), x.shape[1], nh, act,
+                                              arch, be._p(hp), SHIFT[self.gram_shift], be._p(mean), be._p(var),
+                                              be._p(info))
+            if rc != 0:
+                raise RuntimeError("smnngp_predict_mg_f64 failed: " + be.lib.smnngp_mg_last_error().decode())
+            return mean, var, info
         self._Y = y if y.ndim == 2 else y[:, None]
         self._xt = x_test
         self._tab_t, q_t, _ = be.qtable(x_test, self.spec, hp)
@@ -773,6 +795,26 @@ class DistributedPredict(DistributedLML):
         var [T], info), identical on every rank."""
         if self.c != 1:
             raise ValueError("test_nll needs a DistributedPredict built with c = 1")
+        if self.mg is not None:                                    # one C call per rank
+            be = self.be
+            nh, act, arch = self.spec.ids()
+            lik = None
+            if kind == "student_t":
+                if self._lik is None:
+                    self._lik = DistributedLML(self.n, self.d, self.spec, self.a.device, group=self.group, block=self.db,
+                                               backend=self.be, exchange=self.exchange,
+                                               emulate=(self.world, self.rank) if self.emulate else None)
+                lik = self._lik.mg
+            y1 = (y if y.ndim == 1 else y[:, 0]).contiguous()
+            x, x_test, y_test = x.contiguous(), x_test.contiguous(), y_test.contiguous()
+            nll, mean, var = be.empty(1), be.empty(self.t), be.empty(self.t)
+            info = be.zeros(1, dtype=torch.int32)
+            rc = be.lib.smnngp_test_nll_mg_f64(self.mg, lik, be._s(), be._p(x), be._p(y1), be._p(x_test), be._p(y_test),
+                                               x.shape[1], nh, act, arch, be._p(hp), KIND[kind], float(y_mean),
+                                               float(y_std), be._p(nll), be._p(mean), be._p(var), be._p(info))
+            if rc != 0:
+                raise RuntimeError("smnngp_test_nll_mg_f64 failed: " + be.lib.smnngp_mg_last_error().decode())
+            return nll, mean, var, info
         mean, var, info = self.predict(x, y, x_test, hp)
         quad2 = None
         if kind == "student_t":

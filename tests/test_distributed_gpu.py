@@ -128,6 +128,43 @@ def test_single_rank_peer_drivers_match_oracle(n, db, driver, monkeypatch):
     job.close()
 
 
+@pytest.mark.parametrize("driver", ["c", "python"])
+@pytest.mark.parametrize("n,t,c,db", [(1500, 300, 2, 128), (2600, 700, 1, 256), (3000, 200, 3, 512)])
+def test_single_rank_predict_drivers_match_oracle(n, t, c, db, driver, monkeypatch):
+    """NNGPKernel.predict / SPR.test_nll through the distributed drivers at world size 1 (peer-store pipeline, carried
+    right-hand-side and test rows, Z / result exchange through the peer slots): C driver (smnngp_predict_mg_f64,
+    smnngp_test_nll_mg_f64) and Python panel loop against the oracle"""
+    import torch
+    import smnngp_b200 as sm
+    from oracle import nngp_oracle as orc
+    from smnngp_b200.distributed import DistributedPredict
+    from tests.synth import regression_data, DEFAULT_HP as hp
+    monkeypatch.setenv("SMNNGP_MG_DRIVER", driver)
+    d = 8
+    x, y, xt, yt, ym, ys = regression_data(n, d, t=t)
+    rng = np.random.default_rng(5)
+    Y = np.column_stack([y] + [rng.standard_normal(n) for _ in range(c - 1)])
+    spec = sm.StackSpec(3, "relu", "mlp")
+    job = DistributedPredict(n, d, t, c, spec, "cuda", block=db, emulate=(1, 0), exchange="peer")
+    assert (job.mg is not None) == (driver == "c")
+    hpd = sm.make_hp(**hp)
+    xd, Yd, xtd = torch.from_numpy(x).cuda(), torch.from_numpy(Y).cuda(), torch.from_numpy(xt).cuda()
+    kw = dict(num_hiddens=3, act="relu", arch="mlp", w_std=hp["w_std"], b_std=hp["b_std"], last_w_std=hp["last_w_std"])
+    mean_ref, cov_ref = orc.nt_predict(x, Y, xt, hp["eps"], kernel_kwargs=kw)
+    vref, ktt = np.diag(cov_ref), orc.nngp_diag(xt, **kw)
+    for _ in range(2):                                        # second call: sequence numbers / buffers reused
+        mean, var, info = job.predict(xd, Yd, xtd, hpd)
+        mean, var = mean.cpu().numpy(), var.cpu().numpy()
+        assert int(info.item()) == 0
+        assert np.abs(mean - mean_ref).max() <= 1e-8 * np.abs(mean_ref).max()
+        assert np.all(np.abs(var - vref) <= 1e-8 * np.abs(vref) + 1e-13 * ktt)
+    if c == 1:
+        nll, m1, v1, info = job.test_nll(xd, torch.from_numpy(y).cuda(), xtd, torch.from_numpy(yt).cuda(), ym, ys, hpd)
+        ref = orc.spr_test_nll(x, y, xt, yt, ym, ys, eps=hp["eps"], kind="student_t", a=hp["alpha"], b=hp["beta"], **kw)
+        assert int(info.item()) == 0 and abs(float(nll.item()) - ref) <= 1e-8 * abs(ref)
+    job.close()
+
+
 def _predict_worker(rank, world, port, n, t, c, d, db, q, exchange):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
