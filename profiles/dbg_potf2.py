@@ -27,8 +27,11 @@ for _ in range(3):
     be.factor_diag(a, linv, ld, info, 0); torch.cuda.synchronize()
 t = clk.cpu().numpy()
 lib.smnngp_debug_potf2_clocks(C.c_void_p(0))
-d = np.diff(t[: 2 + 3 * (128 // 16) + 2])
-names = ["stage"] + sum([[f"diag{b}", f"panel{b}", f"update{b}"] for b in range(128 // 16)], []) + ["inv-assembly", "write-back"]
+# marks (chol.cu potf2_trtri_kernel): start, staged, diag0, then per block b: panel_b, update_b(+diag_{b+1}), then
+# inverse assembled, written back
+nb = 128 // 16
+d = np.diff(t[: 3 + 2 * nb + 2])
+names = ["stage", "diag0"] + sum([[f"panel{b}", f"update{b}+diag{b + 1}"] for b in range(nb)], []) + ["inv-assembly", "write-back"]
 tot = d.sum()
 print("potf2 phases (cycles):", {n: int(v) for n, v in zip(names, d)})
-print("total cycles", int(tot), "diag sum", int(d[1::3][:8].sum()), "panel sum", int(d[2::3][:8].sum()), "update sum", int(d[3::3][:8].sum()))
+print("total cycles", int(tot), "panel sum", int(d[2::2][:nb].sum()), "update+diag sum", int(d[3::2][:nb].sum()))

@@ -4,7 +4,10 @@ ReLU, Student-t, seed 10, reference CLI defaults) and print / store the loss, so
 (tests/test_gpu_parity.py::test_c3_full_size_matches_oracle_golden, bench.py `parity.full_n_rel_err`).
 
 Same arithmetic as oracle.nngp_oracle.spr_loss (spax/models.py:93-98 -> spax/likelihoods.py:45-50 -> spax/utils.py:
-160-183) written memory-lean: the Gram matrix is scaled and factored in place (one 28.8 GB array instead of three).
+160-183) written memory-lean and in blocks: the Gram matrix is scaled and factored in place (one 28.8 GB array instead
+of three), and the Cholesky / forward substitution run LAPACK potrf / trsm block by block (right-looking, 8192-wide
+panels) because SciPy's 32-bit LAPACK interface segfaults on a single matrix with more than 2^31 elements
+(N >= 46 341).  `--check` compares the blocked path with the one-call path at a size where both work.
 About 3-5 minutes on 16-32 host cores.  Usage:  python tests/golden/make_c3_golden.py [--rows N] [--out file.json]
 """
 import argparse
@@ -21,11 +24,43 @@ import scipy.linalg as sla
 from scipy.special import gammaln
 
 
+def cholesky_blocked_inplace(a, nb=8192):
+    """Lower Cholesky factor of the symmetric a (C-order, lower part read) in place, right-looking by nb-wide panels:
+    LAPACK potrf on the diagonal block, trsm for the panel, gemm for the trailing lower blocks."""
+    n = a.shape[0]
+    for k0 in range(0, n, nb):
+        k1 = min(k0 + nb, n)
+        lkk = sla.cholesky(a[k0:k1, k0:k1], lower=True, check_finite=False)
+        a[k0:k1, k0:k1] = lkk
+        if k1 == n:
+            break
+        panel = a[k1:, k0:k1]
+        panel[...] = sla.solve_triangular(lkk, panel.T, lower=True, check_finite=False).T      # panel L_kk^-T
+        for i0 in range(k1, n, nb):
+            i1 = min(i0 + nb, n)
+            a[i0:i1, k1:i1] -= panel[i0 - k1:i1 - k1] @ panel[:i1 - k1].T
+    return a
+
+
+def forward_substitution_blocked(L, y, nb=8192):
+    """z = L^-1 y with the lower factor stored in the lower part of L (blocks of nb rows)"""
+    n = L.shape[0]
+    z = np.array(y, dtype=np.float64)
+    for k0 in range(0, n, nb):
+        k1 = min(k0 + nb, n)
+        if k0 > 0:
+            z[k0:k1] -= L[k0:k1, :k0] @ z[:k0]
+        z[k0:k1] = sla.solve_triangular(L[k0:k1, k0:k1], z[k0:k1], lower=True, check_finite=False)
+    return z
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=60000)
     ap.add_argument("--features", type=int, default=784)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "c3_golden.json"))
+    ap.add_argument("--block", type=int, default=8192)
+    ap.add_argument("--check", action="store_true", help="also run scipy's one-call path (N < 46 341 only) and compare")
     args = ap.parse_args()
     from oracle import nngp_oracle as orc
     from tests.synth import pixel_data, DEFAULT_HP as hp
@@ -40,11 +75,16 @@ def main():
     cov *= b / a                                                           # spax/likelihoods.py:49
     df = 2 * a
     t = 0.5 * (df + n)
+    ref = None
+    if args.check:
+        Lr = sla.cholesky(cov, lower=True, check_finite=False)
+        zr = sla.solve_triangular(Lr, y, lower=True, check_finite=False)
+        ref = (float(zr @ zr), float(np.log(np.diag(Lr)).sum()))
+        del Lr
     t1 = time.perf_counter()
-    # cov is symmetric: its transpose view is Fortran-ordered, so LAPACK factors it in place (no second copy)
-    L = sla.cholesky(cov.T, lower=True, overwrite_a=True, check_finite=False)   # spax/utils.py:179
+    L = cholesky_blocked_inplace(cov, args.block)                          # spax/utils.py:179
     t_chol = time.perf_counter() - t1
-    z = sla.solve_triangular(L, y, lower=True, check_finite=False)        # spax/utils.py:180
+    z = forward_substitution_blocked(L, y, args.block)                     # spax/utils.py:180
     logp = float(-t * np.log(1.0 + (1.0 / df) * (z @ z)) - n / 2 * np.log(df * np.pi) + gammaln(t)
                  - gammaln(0.5 * df) - np.log(np.diag(L)).sum())          # spax/utils.py:181-183
     loss = -logp / n                                                       # spax/models.py:98
@@ -52,6 +92,9 @@ def main():
            "oracle_quad": float(z @ z), "oracle_sum_log_diag": float(np.log(np.diag(L)).sum()),
            "seconds": {"gram": t_gram, "cholesky": t_chol, "total": time.perf_counter() - t0},
            "host_cpus": os.cpu_count()}
+    if ref is not None:
+        res["check_one_call_vs_blocked"] = {"quad_rel": abs(ref[0] - res["oracle_quad"]) / abs(ref[0]),
+                                            "sum_log_diag_rel": abs(ref[1] - res["oracle_sum_log_diag"]) / abs(ref[1])}
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         json.dump(res, f, indent=1)
