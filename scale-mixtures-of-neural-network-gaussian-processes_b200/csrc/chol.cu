@@ -215,50 +215,41 @@ __device__ __forceinline__ double rsqrt_fast(double d) {
   return fma(y2, fma(-d * y2, y2, 1.0) * 0.5, y2);   // one more Newton step on y = 1/sqrt(d)
 }
 
-// warp 0, lane = row (lanes >= DB idle along): factor the DB x DB block at Gbb (lower part valid), write L back
-// (lower) and inv(L) to M.
-__device__ __forceinline__ void diag_factor_invert(double* __restrict__ Gbb, double* __restrict__ M, int lane,
-                                                   int col_base, int& bad) {
-  const int row = lane < DB ? lane : DB - 1;
-  double a[DB], rinvs[DB];
+// warp 0: factor the DB x DB block at Gbb (lower part valid) in place and write inv(L) to M.
+//   lanes 0 .. DB-1   hold row `lane` of the block,
+//   lanes DB .. 2DB-1 hold row `lane - DB` of the IDENTITY: carried through the same column operations they come out
+//                     as rows of L^-T, i.e. the columns of inv(L) - the inverse costs nothing extra (it used to be a
+//                     separate 16-step forward substitution, ~40 % of this routine's time and half of its code).
+// The pivot loop is ROLLED: after pivot j the register window is rotated (a[c] <- a[c+1]) so that the pivot column is
+// always a[0], and finished columns go straight to shared memory.  The fully unrolled version was ~2000 instructions
+// per call site; this kernel runs every instruction about once per launch, so it was bound by cold instruction fetch
+// (the first diagonal block of a launch took 64 k cycles, the following ones 6 k: profiles/r02_potf2_phases.txt).
+__device__ __noinline__ void diag_factor_invert(double* __restrict__ Gbb, double* __restrict__ M, int lane,
+                                                int col_base, int* bad) {
+  static_assert(2 * DB <= 32, "block rows + carried identity rows must fit one warp");
+  const bool is_row = lane < DB;
+  const int r = is_row ? lane : lane - DB;               // block row, or the identity row this lane carries
+  double a[DB];
 #pragma unroll
-  for (int c = 0; c < DB; c++) a[c] = Gbb[row * GLD + c];
-#pragma unroll
+  for (int c = 0; c < DB; c++) a[c] = is_row ? Gbb[r * GLD + c] : (c == r ? 1.0 : 0.0);
+#pragma unroll 1
   for (int j = 0; j < DB; j++) {
-    double d = shfl_d(a[j], j);
-    if (!(d > 0.0)) {                 // non-PD (or NaN input): mirror lax.linalg.cholesky -> NaN, no abort
-      if (bad == 0) bad = col_base + j + 1;
+    double d = shfl_d(a[0], j);                          // pivot: row j, column j
+    if (!(d > 0.0)) {                                    // non-PD (or NaN input): mirror lax.linalg.cholesky -> NaN
+      if (*bad == 0) *bad = col_base + j + 1;
       d = __longlong_as_double(0x7ff8000000000000ll);
     }
-    const double rinv = rsqrt_fast(d);
-    rinvs[j] = rinv;                                          // = 1 / L_jj (same value in every lane)
-    const double l = (lane == j) ? d * rinv : a[j] * rinv;   // lane j: L_jj = sqrt(d); lanes > j: L_ij
-    a[j] = l;
-#pragma unroll
-    for (int c = j + 1; c < DB; c++) a[c] = fma(-l, shfl_d(l, c), a[c]);
-  }
-  if (lane < DB) {
-#pragma unroll
-    for (int c = 0; c < DB; c++)
-      if (c <= lane) Gbb[lane * GLD + c] = a[c];
-  }
-  __syncwarp();
-  // inverse, lane = column c: x_i = (delta_ic - sum_{k=c}^{i-1} L_ik x_k) * (1 / L_ii)   (L_ik: broadcast reads)
-  double x[DB];
-#pragma unroll
-  for (int i = 0; i < DB; i++) {
-    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
-#pragma unroll
-    for (int k = 0; k < i; k += 2) {
-      s0 = fma(-Gbb[i * GLD + k], x[k], s0);
-      if (k + 1 < i) s1 = fma(-Gbb[i * GLD + k + 1], x[k + 1], s1);
+    const double rinv = rsqrt_fast(d);                   // = 1 / L_jj (same value in every lane)
+    const double l = (lane == j) ? d * rinv : a[0] * rinv;     // column j of L (rows >= j) / of the carried rows
+    if (is_row) {
+      if (r >= j) Gbb[r * GLD + j] = l;
+    } else {
+      M[j * MLD + r] = (r <= j) ? l : 0.0;               // inv(L)[j][r] = (L^-T)[r][j]; zero above the diagonal
     }
-    const double v = (s0 + s1) * rinvs[i];
-    x[i] = (i >= lane) ? v : 0.0;     // rows above the column's diagonal stay exactly zero
-  }
-  if (lane < DB) {
+    // rank-1 update of the remaining columns, rotated one slot to the left: new a[c-1] = column j + c
 #pragma unroll
-    for (int i = 0; i < DB; i++) M[i * MLD + lane] = x[i];
+    for (int c = 1; c < DB; c++) a[c - 1] = fma(-l, shfl_d(l, (j + c) & (DB - 1)), a[c]);
+    a[DB - 1] = 0.0;                                     // slots past the last column: never reach a[0] as a pivot
   }
 }
 
@@ -321,7 +312,7 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
   // warp 0 updates ONLY the next diagonal block and factors it while warps 1..7 apply the rest of block b's trailing
   // update - the update hides under the pivot chain instead of adding to it.
   int bad = 0;
-  if (warp == 0) diag_factor_invert(G, Mi, lane, 0, bad);
+  if (warp == 0) diag_factor_invert(G, Mi, lane, 0, &bad);
   __syncthreads();
   PF_CLK();   // diag 0
   for (int b = 0; b < nblk; b++) {
@@ -371,7 +362,7 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
         }
       }
       __syncwarp();
-      if (b + 1 < nblk) diag_factor_invert(G + r_first * GLD + r_first, Mi + (b + 1) * DB * MLD, lane, r_first, bad);
+      if (b + 1 < nblk) diag_factor_invert(G + r_first * GLD + r_first, Mi + (b + 1) * DB * MLD, lane, r_first, &bad);
     } else {
       for (int s = NT + (warp - 1); s < nstrips; s += PF_WARPS - 1) {
         const int r0 = r_first + s * 8;
@@ -443,6 +434,7 @@ potf2_trtri_kernel(double* __restrict__ A, long long lda, int w, double* __restr
 
   // write back: L and inv(L), lower parts only (the strict upper triangle of A is never touched; the part of
   // the inverse above the diagonal is zero and the workspace block was zero-filled when the factorisation began)
+#pragma unroll 4
   for (int idx = tid; idx < wp * (PB / 2); idx += PF_THREADS) {
     const int i = idx >> 6, c = (idx & 63) * 2;
     if (c > i) continue;
