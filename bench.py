@@ -49,11 +49,12 @@ CPU_SAMPLE_N = 20000
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from an `ncu --set full` capture.
 # It is NOT measured by this run (nothing is timed under a profiler): the capture it comes from, the launch it
 # belongs to and that launch's algorithmic bytes are named so the figure can be compared like for like.
-TRAFFIC = {"traffic": 2.644e9,
-           "traffic_launch": "potrf N=16384, first outer trailing update (n=15872, K=512): 1.29e11 flop, algorithmic "
-                             "bytes 2.08e9 (C lower tiles read+write 8 n (n+1) + panel 8 n K) - a different launch than "
-                             "the ones timed here (round-1 capture)",
-           "traffic_source": "profiles/r01_update_tma_ncu_summary.txt"}
+TRAFFIC = {"traffic": 7.021e10,
+           "traffic_launch": "C3 (N=60000), FIRST outer trailing update (n=59488, K=512): 1.812e12 flop, algorithmic bytes "
+                             "2.855e10 (C lower tiles read+write 8 n (n+1) + panel 8 n K), dram read 5.607e10 + write "
+                             "1.414e10; the timed region averages over all 116 update launches of a step, this is the "
+                             "largest one (round-2 capture, not measured by this run)",
+           "traffic_source": "profiles/r02_update_ncu_summary.txt"}
 
 
 def lml_flops(n, d):

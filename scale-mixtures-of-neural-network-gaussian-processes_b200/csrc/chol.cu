@@ -219,11 +219,12 @@ __device__ __forceinline__ double rsqrt_fast(double d) {
 //   lanes 0 .. DB-1   hold row `lane` of the block,
 //   lanes DB .. 2DB-1 hold row `lane - DB` of the IDENTITY: carried through the same column operations they come out
 //                     as rows of L^-T, i.e. the columns of inv(L) - the inverse costs nothing extra (it used to be a
-//                     separate 16-step forward substitution, ~40 % of this routine's time and half of its code).
-// The pivot loop is ROLLED: after pivot j the register window is rotated (a[c] <- a[c+1]) so that the pivot column is
-// always a[0], and finished columns go straight to shared memory.  The fully unrolled version was ~2000 instructions
-// per call site; this kernel runs every instruction about once per launch, so it was bound by cold instruction fetch
-// (the first diagonal block of a launch took 64 k cycles, the following ones 6 k: profiles/r02_potf2_phases.txt).
+//                     separate 16-step forward substitution: ~40 % of this routine's time and half of its code).
+// The pivot loop stays fully unrolled (ptxas interleaves pivot j's remaining column updates with pivot j+1's
+// rsqrt chain; a rolled loop with a rotating register window measured 580 cycles per pivot against ~200 unrolled:
+// profiles/r02_potf2_phases.txt) but the routine is a single out-of-line copy (~800 instructions) instead of two inlined
+// ~2000-instruction ones: this kernel runs every instruction about once per launch, so its first diagonal block was
+// bound by cold instruction fetch (64 k cycles, the following blocks 6 k).
 __device__ __noinline__ void diag_factor_invert(double* __restrict__ Gbb, double* __restrict__ M, int lane,
                                                 int col_base, int* bad) {
   static_assert(2 * DB <= 32, "block rows + carried identity rows must fit one warp");
@@ -232,24 +233,29 @@ __device__ __noinline__ void diag_factor_invert(double* __restrict__ Gbb, double
   double a[DB];
 #pragma unroll
   for (int c = 0; c < DB; c++) a[c] = is_row ? Gbb[r * GLD + c] : (c == r ? 1.0 : 0.0);
-#pragma unroll 1
+  int first_bad = 0;
+#pragma unroll
   for (int j = 0; j < DB; j++) {
-    double d = shfl_d(a[0], j);                          // pivot: row j, column j
+    double d = shfl_d(a[j], j);                          // pivot: row j, column j
     if (!(d > 0.0)) {                                    // non-PD (or NaN input): mirror lax.linalg.cholesky -> NaN
-      if (*bad == 0) *bad = col_base + j + 1;
+      if (first_bad == 0) first_bad = col_base + j + 1;
       d = __longlong_as_double(0x7ff8000000000000ll);
     }
     const double rinv = rsqrt_fast(d);                   // = 1 / L_jj (same value in every lane)
-    const double l = (lane == j) ? d * rinv : a[0] * rinv;     // column j of L (rows >= j) / of the carried rows
-    if (is_row) {
-      if (r >= j) Gbb[r * GLD + j] = l;
-    } else {
-      M[j * MLD + r] = (r <= j) ? l : 0.0;               // inv(L)[j][r] = (L^-T)[r][j]; zero above the diagonal
-    }
-    // rank-1 update of the remaining columns, rotated one slot to the left: new a[c-1] = column j + c
+    const double l = (lane == j) ? d * rinv : a[j] * rinv;     // column j of L (rows >= j) / of the carried rows
+    a[j] = l;
 #pragma unroll
-    for (int c = 1; c < DB; c++) a[c - 1] = fma(-l, shfl_d(l, (j + c) & (DB - 1)), a[c]);
-    a[DB - 1] = 0.0;                                     // slots past the last column: never reach a[0] as a pivot
+    for (int c = j + 1; c < DB; c++) a[c] = fma(-l, shfl_d(l, c), a[c]);
+  }
+  if (first_bad != 0 && *bad == 0) *bad = first_bad;
+  if (is_row) {
+#pragma unroll
+    for (int c = 0; c < DB; c++)
+      if (c <= r) Gbb[r * GLD + c] = a[c];
+  } else {
+    // inv(L)[c][r] = (L^-T)[r][c], zero above the diagonal
+#pragma unroll
+    for (int c = 0; c < DB; c++) M[c * MLD + r] = (c >= r) ? a[c] : 0.0;
   }
 }
 
