@@ -258,6 +258,7 @@ int smnngp_mg_connect_ptrs(smnngp_mg* g, void* const* regions, const int* peer_d
 int smnngp_mg_connect_emulated(smnngp_mg* g);
 void smnngp_mg_set_timeout(smnngp_mg* g, double seconds);
 void smnngp_mg_set_sm_reserve(smnngp_mg* g, int sms);         /* < 0: automatic (default) */
+void smnngp_mg_set_reserve_margin(smnngp_mg* g, double margin); /* automatic reserve = margin * 82.5 w / ncols + 3 (4.5) */
 void smnngp_mg_timeline(smnngp_mg* g, int enable);            /* profiling: CUDA events at the stage boundaries */
 int smnngp_mg_timeline_read(smnngp_mg* g, int cap, int* panel_out, int* label_out, double* ms_out);
 const char* smnngp_mg_last_error(void);

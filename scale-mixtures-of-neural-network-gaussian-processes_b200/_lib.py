@@ -39,7 +39,7 @@ EXPORTS = [
     "smnngp_instr_reset", "smnngp_instr_launches", "smnngp_instr_updates", "smnngp_dmma_peak_tflops",
     "smnngp_stage_assemble_inverse_f64",
     "smnngp_mg_create", "smnngp_mg_destroy", "smnngp_mg_ipc_handle", "smnngp_mg_region", "smnngp_mg_connect_ipc",
-    "smnngp_mg_connect_ptrs", "smnngp_mg_connect_emulated", "smnngp_mg_set_timeout", "smnngp_mg_set_sm_reserve",
+    "smnngp_mg_connect_ptrs", "smnngp_mg_connect_emulated", "smnngp_mg_set_timeout", "smnngp_mg_set_sm_reserve", "smnngp_mg_set_reserve_margin",
     "smnngp_mg_timeline", "smnngp_mg_timeline_read", "smnngp_mg_last_error", "smnngp_lml_mg_f64",
     "smnngp_mg_create_predict", "smnngp_predict_mg_f64", "smnngp_test_nll_mg_f64",
 ]
@@ -102,6 +102,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
         finally:
             fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
+
+
+XLA_LIB_PATH = os.path.join(LIB_DIR, "libsmnngp_xla.so")
+
+
+def build_xla_shim(force: bool = False) -> str:
+    """Compile csrc/xla_ffi_c_shim.c (XLA FFI handlers over the C-ABI, plain-C call-frame level) into
+    lib/libsmnngp_xla.so with gcc.  Without jaxlib it is built against the locally re-declared subset of
+    xla/ffi/api/c_api.h (csrc/xla_ffi_min/); with SMNNGP_XLA_FFI_INCLUDE=<jaxlib include dir> against the real header."""
+    src = os.path.join(CSRC, "xla_ffi_c_shim.c")
+    deps = [src, os.path.join(CSRC, "xla_ffi_min", "c_api_subset.h"), os.path.join(_HERE, "..", "include", "smnngp.h")]
+    if not force and os.path.exists(XLA_LIB_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(XLA_LIB_PATH) for d in deps):
+        return XLA_LIB_PATH
+    build()
+    cmd = ["gcc", "-O2", "-std=c11", "-Wall", "-Werror", "-fPIC", "-shared", src, "-I", CSRC]
+    real = os.environ.get("SMNNGP_XLA_FFI_INCLUDE")
+    if real:
+        cmd += ["-DSMNNGP_USE_REAL_XLA_FFI", "-I", real]
+    tmp = XLA_LIB_PATH + f".tmp{os.getpid()}"
+    cmd += ["-L", LIB_DIR, "-lsmnngp", "-Wl,-rpath,$ORIGIN", "-o", tmp]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"gcc failed on xla_ffi_c_shim.c:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, XLA_LIB_PATH)
+    return XLA_LIB_PATH
 
 
 _lib = None
@@ -204,6 +229,8 @@ def _declare(lib):
     lib.smnngp_mg_connect_emulated.argtypes = [_vp]
     lib.smnngp_mg_set_timeout.restype = None
     lib.smnngp_mg_set_timeout.argtypes = [_vp, _d]
+    lib.smnngp_mg_set_reserve_margin.restype = None
+    lib.smnngp_mg_set_reserve_margin.argtypes = [_vp, _d]
     lib.smnngp_mg_set_sm_reserve.restype = None
     lib.smnngp_mg_set_sm_reserve.argtypes = [_vp, _i]
     lib.smnngp_mg_timeline.restype = None

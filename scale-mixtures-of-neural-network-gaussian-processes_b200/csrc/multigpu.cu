@@ -78,6 +78,7 @@ struct smnngp_mg {
   cudaEvent_t ev_panel = nullptr, ev_a = nullptr, ev_fork = nullptr, ev_done = nullptr;
   // tuning
   int sm_reserve_override = -1;
+  double reserve_margin = 4.5;            // see factor_all: SMs left to the look-ahead chain = margin * 82.5 w / ncols + 3
   double timeout_s = 20.0;
   // timeline (profiling)
   bool timeline_on = false;
@@ -482,6 +483,9 @@ void smnngp_mg_set_timeout(smnngp_mg* g, double seconds) {
 void smnngp_mg_set_sm_reserve(smnngp_mg* g, int sms) {
   if (g) g->sm_reserve_override = sms;
 }
+void smnngp_mg_set_reserve_margin(smnngp_mg* g, double margin) {
+  if (g && margin > 0.0) g->reserve_margin = margin;
+}
 void smnngp_mg_timeline(smnngp_mg* g, int enable) {
   if (!g) return;
   for (auto& m : g->marks) cudaEventDestroy(m.ev);
@@ -579,7 +583,7 @@ int factor_all(smnngp_mg* g, cudaStream_t s, const double* X, const double* y, c
       // update flops 2 m ncols w at 33 TF/s -> 82.5 w / ncols, independent of m and P; x4.5 measured margin + 3
       int reserve = g->sm_reserve_override;
       if (reserve < 0) {
-        reserve = P > 1 || g->emulate ? (int)(4.5 * 82.5 * (double)w / (double)(n - c1 - na)) + 3 : 0;
+        reserve = P > 1 || g->emulate ? (int)(g->reserve_margin * 82.5 * (double)w / (double)(n - c1 - na)) + 3 : 0;
         if (P > 1 || g->emulate) reserve = std::min(32, std::max(2, reserve));
       }
       MG_RC(smnngp_stage_update_f64(s, arows, db, pfull + na * db, db, g->a + ls * g->ld + c1 + na, g->ld, m,

@@ -264,6 +264,8 @@ class PeerExchange:
 
 def default_block(n, world):
     """distribution block = outer panel width: wide enough for the update kernel, small enough to balance"""
+    if os.environ.get("SMNNGP_BLOCK"):                       # tuning experiments
+        return int(os.environ["SMNNGP_BLOCK"])
     per_rank = n / max(world, 1)
     if per_rank >= 4096:
         return 512
@@ -398,6 +400,8 @@ class DistributedLML:
             lib.smnngp_mg_set_timeout(h, float(os.environ.get("SMNNGP_PEER_TIMEOUT_S", "20")))
             if "SMNNGP_SM_RESERVE" in os.environ:
                 lib.smnngp_mg_set_sm_reserve(h, int(os.environ["SMNNGP_SM_RESERVE"]))
+            if "SMNNGP_RESERVE_MARGIN" in os.environ:
+                lib.smnngp_mg_set_reserve_margin(h, float(os.environ["SMNNGP_RESERVE_MARGIN"]))
         self.mg = h                               # the row shard lives inside the handle
 
     LABELS = ("diag", "bcast", "trsm", "gather", "main_start", "update_a", "update_b", "start")
