@@ -219,6 +219,17 @@ int smnngp_stage_push_panel_f64(void* stream, const double* Ploc, int64_t m, int
 /* how wait_flags waits: 0 (default) = cuStreamWaitValue64 on the stream (no SM occupied, no timeout), 1 = one-thread
  * spin kernel with the timeout described above */
 void smnngp_set_peer_wait_mode(int mode);
+/* variants for the snake (boustrophedon) block distributions of csrc/multigpu.cu: cyc_alt = extra column shift of the
+ * rows of odd local blocks in the update mask; even_off / odd_off: the global block of this rank's local block lb is
+ * lb * P + (lb odd ? odd_off : even_off)  (plain cyclic: both = rank) */
+int smnngp_stage_update2_f64(void* stream, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                             int64_t ldc, int64_t M, int64_t N, int64_t K, int lower, int64_t cyc_db, int64_t cyc_p,
+                             int64_t base_shift, int64_t cyc_alt, int sm_reserve);
+int smnngp_stage_trsm_scatter2_f64(void* stream, const double* R, int64_t ldr, int64_t m, int64_t w, const double* W,
+                                   int64_t ldw, double* Ploc, int64_t ldp, void* const* peer_ptrs, int P, int rank,
+                                   int64_t db, int64_t local_row0, int64_t c1, int64_t n, int64_t ld_peer,
+                                   void* const* flag_ptrs, int64_t flag_index, uint64_t seq, unsigned int* counter,
+                                   int64_t even_off, int64_t odd_off);
 int smnngp_stage_trsm_scatter_f64(void* stream, const double* R, int64_t ldr, int64_t m, int64_t w, const double* W,
                                   int64_t ldw, double* Ploc, int64_t ldp, void* const* peer_ptrs, int P, int rank,
                                   int64_t db, int64_t local_row0, int64_t c1, int64_t n, int64_t ld_peer,

@@ -37,7 +37,7 @@ EXPORTS = [
     "smnngp_stage_push_panel_f64",
     "smnngp_peer_alloc", "smnngp_peer_open", "smnngp_peer_close", "smnngp_peer_free",
     "smnngp_instr_reset", "smnngp_instr_launches", "smnngp_instr_updates", "smnngp_dmma_peak_tflops",
-    "smnngp_stage_assemble_inverse_f64",
+    "smnngp_stage_assemble_inverse_f64", "smnngp_stage_update2_f64", "smnngp_stage_trsm_scatter2_f64",
     "smnngp_mg_create", "smnngp_mg_destroy", "smnngp_mg_ipc_handle", "smnngp_mg_region", "smnngp_mg_connect_ipc",
     "smnngp_mg_connect_ptrs", "smnngp_mg_connect_emulated", "smnngp_mg_set_timeout", "smnngp_mg_set_sm_reserve", "smnngp_mg_set_reserve_margin",
     "smnngp_mg_timeline", "smnngp_mg_timeline_read", "smnngp_mg_last_error", "smnngp_lml_mg_f64",

@@ -137,6 +137,7 @@ cudaError_t launch_gemm_tma(cudaStream_t s, const GemmParams& p) {
   const int tri = p.lower && p.cyc_db == 0;
   TmaShape sh{p.M, p.N, p.K, tri, count_tiles<TileTma>(p.M, p.N, tri), p.lower ? p.cyc_db : 0, p.cyc_p, p.base_shift,
               p.k_from_row, p.k_upto_col};
+  sh.cyc_alt = p.lower ? p.cyc_alt : 0;
   if (sh.cyc_db != 0) sh.tiles = tma_cyc_count_tiles(sh);       // active tiles only
   int sms = device_sm_count() - p.sm_reserve;
   if (sms < 8) sms = 8;

@@ -33,6 +33,7 @@ struct ScatterParams {
   long long local_row0;         // local row index of R's first row (local storage order)
   long long c1, n;              // first global row held by the panel buffers; rows >= n (the y^T row) stay local
   int db, P, rank;
+  long long even_off, odd_off;  // global block of local block lb = lb * P + (lb odd ? odd_off : even_off)  (cyclic: rank)
   PeerSignal sig;
 };
 
@@ -47,7 +48,8 @@ struct EpiScatterTma {
       const int r = rbase + mi * 8;
       if (r >= p.g.M) continue;
       const long long lr = p.local_row0 + r;
-      const long long g = ((lr / p.db) * p.P + p.rank) * p.db + lr % p.db;     // global row of this local row
+      const long long lb = lr / p.db;                                        // global row of this local row
+      const long long g = (lb * p.P + ((lb & 1) ? p.odd_off : p.even_off)) * p.db + lr % p.db;
       const bool remote = g < p.n;
       const long long prow = (g - p.c1) * p.ld_peer;
 #pragma unroll
@@ -305,10 +307,11 @@ void smnngp_set_peer_wait_mode(int mode) { wait_mode() = mode ? 1 : 0; }
 // Panel solve + all-gather in one kernel:  Ploc [m, ldp] = R [m, w] W^T  and the same rows stored at their global
 // position (global row - c1) of every rank's panel buffer; then this rank's flag (index flag_index) is raised on
 // every rank.  local_row0 = local storage index of R's first row; rows whose global index is >= n stay local.
-int smnngp_stage_trsm_scatter_f64(void* stream, const double* R, int64_t ldr, int64_t m, int64_t w, const double* W,
+int smnngp_stage_trsm_scatter2_f64(void* stream, const double* R, int64_t ldr, int64_t m, int64_t w, const double* W,
                                   int64_t ldw, double* Ploc, int64_t ldp, void* const* peer_ptrs, int P, int rank,
                                   int64_t db, int64_t local_row0, int64_t c1, int64_t n, int64_t ld_peer,
-                                  void* const* flag_ptrs, int64_t flag_index, uint64_t seq, unsigned int* counter) {
+                                  void* const* flag_ptrs, int64_t flag_index, uint64_t seq, unsigned int* counter,
+                                   int64_t even_off, int64_t odd_off) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Enter scope(s);
   if (!W || !peer_ptrs || !flag_ptrs || !counter || P < 1 || P > MAX_PEERS || m < 0 || w <= 0 ||
@@ -322,7 +325,7 @@ int smnngp_stage_trsm_scatter_f64(void* stream, const double* R, int64_t ldr, in
   sp.g.M = (int)m; sp.g.N = (int)w; sp.g.K = (int)w;
   for (int q = 0; q < P; q++) sp.peer[q] = static_cast<double*>(peer_ptrs[q]);
   sp.ld_peer = ld_peer; sp.local_row0 = local_row0; sp.c1 = c1; sp.n = n;
-  sp.db = (int)db; sp.P = P; sp.rank = rank;
+  sp.db = (int)db; sp.P = P; sp.rank = rank; sp.even_off = even_off; sp.odd_off = odd_off;
   fill_signal(sp.sig, flag_ptrs, P, flag_index, seq, counter);
   CUtensorMap ma, mb;
   if (!make_tmap(&ma, R, m, w, ldr, TM_BM) || !make_tmap(&mb, W, w, w, ldw, TM_BN)) return SMNNGP_ECUDA;
@@ -330,6 +333,14 @@ int smnngp_stage_trsm_scatter_f64(void* stream, const double* R, int64_t ldr, in
   cudaError_t e = launch_tma_gemm<EpiScatterTma>(s, ma, mb, sh, sp, device_sm_count());
   instr().launches++;
   return e == cudaSuccess ? SMNNGP_OK : SMNNGP_ECUDA;
+}
+
+int smnngp_stage_trsm_scatter_f64(void* stream, const double* R, int64_t ldr, int64_t m, int64_t w, const double* W,
+                                  int64_t ldw, double* Ploc, int64_t ldp, void* const* peer_ptrs, int P, int rank,
+                                  int64_t db, int64_t local_row0, int64_t c1, int64_t n, int64_t ld_peer,
+                                  void* const* flag_ptrs, int64_t flag_index, uint64_t seq, unsigned int* counter) {
+  return smnngp_stage_trsm_scatter2_f64(stream, R, ldr, m, w, W, ldw, Ploc, ldp, peer_ptrs, P, rank, db, local_row0, c1, n,
+                                        ld_peer, flag_ptrs, flag_index, seq, counter, rank, rank);
 }
 
 }  // extern "C"

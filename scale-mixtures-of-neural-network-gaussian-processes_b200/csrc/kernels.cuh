@@ -52,13 +52,17 @@ struct GemmParams {
   int sm_reserve;     // persistent kernel leaves this many SMs free (look-ahead work on another stream)
   int k_from_row;     // 1: contraction of the tile whose first row is r0 starts at k = r0 (operands upper triangular)
   int k_upto_col;     // 1: B is lower triangular - the contraction of the tile whose first column is c0 stops at c0 + 64
+  // snake (boustrophedon) block distribution: consecutive local blocks are alternately (P - 1 - 2 rank) blocks
+  // closer / further apart than P; rows of ODD local blocks (counted from the first row of C) get this extra shift
+  int cyc_alt;
 };
 
 // largest active column of local row r (rows are non-decreasing in this limit)
 __host__ __device__ __forceinline__ long long diag_limit(const GemmParams& p, int r) {
   if (!p.lower) return (1ll << 40);
   if (p.cyc_db == 0) return r;
-  return (long long)r + p.base_shift + (long long)(r / p.cyc_db) * (p.cyc_p - 1) * p.cyc_db;
+  const int lb = r / p.cyc_db;
+  return (long long)r + p.base_shift + (long long)lb * (p.cyc_p - 1) * p.cyc_db + ((lb & 1) ? p.cyc_alt : 0);
 }
 
 // ---- NNGP Gram -------------------------------------------------------------------------------------------

@@ -24,6 +24,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -92,27 +93,80 @@ struct smnngp_mg {
   std::chrono::steady_clock::time_point dog_deadline;
   int* dog_info = nullptr;
 
-  // ---- layout (same rules as distributed.BlockRowCyclic) ----
-  int owner(long long b) const { return (int)(b % P); }
+  // ---- layout: which rank owns which global block (rows [b DB, (b+1) DB)); local storage keeps a rank's blocks in
+  // global order.  Three block -> rank maps, all of the form  block(LB) = LB * P + (LB odd ? odd_off : even_off)  for the
+  // LB-th local block of a rank (that is the only property the kernels rely on: exchange.cu scatter epilogue, update
+  // mask), tabulated once at creation:
+  //   cyclic    : b mod P                                   (distributed.BlockRowCyclic, the Python drivers)
+  //   snake     : odd cycles of P blocks run backwards
+  //   snake_end : the same, but the cycles are aligned to the END of the matrix (default for P > 1).
+  // Why: in the lower-triangular update a block row's work grows with the square of its global index, so with the
+  // plain order the rank at the end of each cycle always holds the widest block: 9 % more update flops than the mean
+  // over a factorisation of 118 blocks on 8 ranks (max / mean 1.091), and every rank waits for it at every panel.
+  // The snake pairs a wide block with a narrow one; aligning the cycles to the end puts the one incomplete cycle where
+  // the blocks are cheap (max / mean 1.054 start-aligned, 1.0075 end-aligned at 118 blocks).
+  int layout = 0;                                   // 0 cyclic, 1 snake, 2 snake_end
+  std::vector<int> owner_tab;                       // [nblocks]
+  std::vector<long long> lb_tab;                    // [nblocks] local block index on the owner
+  std::vector<std::vector<long long>> blocks;       // [P][local blocks] global block ids, ascending
+  long long even_off = 0, odd_off = 0;              // this rank's block(LB) formula (see above)
+
+  bool build_layout() {
+    owner_tab.assign((size_t)nblocks, 0);
+    lb_tab.assign((size_t)nblocks, 0);
+    blocks.assign((size_t)P, {});
+    for (long long b = 0; b < nblocks; b++) {
+      const long long bb = layout == 2 ? nblocks - 1 - b : b;
+      const int j = (int)(bb % P);
+      owner_tab[b] = (layout != 0 && ((bb / P) & 1)) ? P - 1 - j : j;
+    }
+    for (long long b = 0; b < nblocks; b++) {
+      lb_tab[b] = (long long)blocks[owner_tab[b]].size();
+      blocks[owner_tab[b]].push_back(b);
+    }
+    const auto& mine = blocks[rank];
+    even_off = mine.empty() ? rank : mine[0];
+    odd_off = mine.size() > 1 ? mine[1] - P : even_off;
+    for (size_t LB = 0; LB < mine.size(); LB++)
+      if (mine[LB] != (long long)LB * P + ((LB & 1) ? odd_off : even_off)) return false;
+    return true;
+  }
+  long long blk(long long LB, int r) const {        // LB-th local block of rank r; past the end: a block id >= nblocks
+    return LB < (long long)blocks[r].size() ? blocks[r][LB] : nblocks + LB;
+  }
+  int owner(long long b) const { return owner_tab[b]; }
   long long block_rows(long long b) const { return std::min((b + 1) * db, mtotal) - b * db; }
   long long local_rows(int r) const {
     long long s = 0;
-    for (long long b = r; b < nblocks; b += P) s += block_rows(b);
+    for (long long b : blocks[r]) s += block_rows(b);
     return s;
   }
   long long local_offset(long long b) const {          // local row offset of global block b on its owner
+    const auto& v = blocks[owner_tab[b]];
     long long s = 0;
-    for (long long x = owner(b); x < b; x += P) s += block_rows(x);
+    for (long long LB = 0; LB < lb_tab[b]; LB++) s += block_rows(v[LB]);
     return s;
   }
-  long long first_block_from(long long gb, int r) const { return gb + (((r - gb) % P) + P) % P; }
+  long long first_block_from(long long gb, int r) const {   // smallest block >= gb owned by r (>= nblocks: none)
+    for (long long b : blocks[r])
+      if (b >= gb) return b;
+    return nblocks;
+  }
   void rows_from_block(long long gb, int r, long long& off, long long& cnt) const {
-    const long long fb = first_block_from(gb, r);
-    const long long all = local_rows(r);
-    if (fb >= nblocks) { off = all; cnt = 0; return; }
     off = 0;
-    for (long long x = r; x < fb; x += P) off += block_rows(x);
-    cnt = all - off;
+    for (long long b : blocks[r]) {
+      if (b >= gb) break;
+      off += block_rows(b);
+    }
+    cnt = local_rows(r) - off;
+  }
+  // extra column shift of the rows of ODD local blocks (counted from the update's first row, which belongs to block
+  // gb0) in the update mask: consecutive local blocks are alternately closer / further apart than P (GemmParams)
+  long long cyc_alt(long long gb0) const {
+    if (gb0 >= nblocks) return 0;
+    const auto& v = blocks[owner_tab[gb0]];
+    const long long LB0 = lb_tab[gb0];
+    return LB0 + 1 < (long long)v.size() ? (v[LB0 + 1] - gb0 - P) * db : 0;
   }
   unsigned long long* flags_local() const { return reinterpret_cast<unsigned long long*>(region + off_flags); }
   double* w_local() const { return reinterpret_cast<double*>(region + off_w); }
@@ -269,9 +323,9 @@ int panel_step(smnngp_mg* g, cudaStream_t s, long long p, int* info_dev, long lo
     g->rows_from_block(p + 1, g->rank, ls, m);
   }
   double* ploc = g->ploc[p & 1];
-  MG_RC(smnngp_stage_trsm_scatter_f64(s, g->a + ls * g->ld + c0, g->ld, m, w, g->w_local(), db, ploc, db, panel_ptrs, P,
-                                      g->rank, db, ls, c1, n, db, flag_ptrs, FLAG_PANEL + g->rank, seq,
-                                      g->counters + 4));
+  MG_RC(smnngp_stage_trsm_scatter2_f64(s, g->a + ls * g->ld + c0, g->ld, m, w, g->w_local(), db, ploc, db, panel_ptrs, P,
+                                       g->rank, db, ls, c1, n, db, flag_ptrs, FLAG_PANEL + g->rank, seq,
+                                       g->counters + 4, g->even_off, g->odd_off));
   mark(g, s, (int)p, 2);                                                          // trsm
   // carried rows (global index >= n: y^T / Y^T rows, test-train cross-Gram rows) are the tail of the local storage:
   // their solved panel columns only exist in ploc - keep them
@@ -308,7 +362,8 @@ int build_gram(smnngp_mg* g, cudaStream_t s, const double* X, const double* y, c
     }
     MG_RC(smnngp_stage_qtable_f64(s, xt, g->t, D, nh, act, arch, hp, g->tab_t, g->t, g->q_t, nullptr));
   }
-  for (long long b = g->rank; b < g->nblocks; b += g->P) {
+  for (long long LB = 0; g->blk(LB, g->rank) < g->nblocks; LB++) {
+    const long long b = g->blk(LB, g->rank);
     const long long g0 = b * db, lo = g->local_offset(b);
     const long long rows = std::min(g0 + g->block_rows(b), n) - g0;          // rows of the square part in this block
     if (rows > 0) {
@@ -354,9 +409,20 @@ static int mg_create_impl(smnngp_mg** out, int rank, int world, int64_t n, int64
   cudaGetDevice(&g->device);
   g->mtotal = n + g->extra;
   g->nblocks = cdiv(g->mtotal, g->db);
+  {
+    const char* lay = getenv("SMNNGP_MG_LAYOUT");     // cyclic | snake | snake_end (default)
+    g->layout = world == 1 ? 0 : 2;
+    if (lay != nullptr && strcmp(lay, "cyclic") == 0) g->layout = 0;
+    if (lay != nullptr && strcmp(lay, "snake") == 0 && world > 1) g->layout = 1;
+    if (!g->build_layout()) {                         // (cannot happen for the three maps above)
+      g->layout = 0;
+      g->build_layout();
+    }
+  }
   g->ld = cdiv(n, 16) * 16;
   g->mloc = g->local_rows(rank);
-  for (long long b = rank; b < g->nblocks; b += world) {      // local rows with global index < n
+  for (long long LB = 0; g->blk(LB, rank) < g->nblocks; LB++) {      // local rows with global index < n
+    const long long b = g->blk(LB, rank);
     const long long g0 = b * g->db, g1 = g0 + g->block_rows(b);
     g->extra_lo += std::max<long long>(0, std::min<long long>(g1, n) - g0);
   }
@@ -570,8 +636,10 @@ int factor_all(smnngp_mg* g, cudaStream_t s, const double* X, const double* y, c
     const long long gb0 = g->first_block_from(p + 1, g->rank);
     const long long shiftc = gb0 * db - c1;
     const long long na = std::min(db, n - c1);                     // next panel's block column first
+    const long long alt = g->cyc_alt(gb0);
     if (m > 0)
-      MG_RC(smnngp_stage_update_f64(s, arows, db, pfull, db, g->a + ls * g->ld + c1, g->ld, m, na, w, 1, db, P, shiftc, 0));
+      MG_RC(smnngp_stage_update2_f64(s, arows, db, pfull, db, g->a + ls * g->ld + c1, g->ld, m, na, w, 1, db, P, shiftc,
+                                     alt, 0));
     mark(g, s, (int)p, 5);                                           // update_a
     MG_CU(cudaEventRecord(g->ev_a, s));
     MG_CU(cudaStreamWaitEvent(g->side, g->ev_a, 0));
@@ -586,8 +654,8 @@ int factor_all(smnngp_mg* g, cudaStream_t s, const double* X, const double* y, c
         reserve = P > 1 || g->emulate ? (int)(g->reserve_margin * 82.5 * (double)w / (double)(n - c1 - na)) + 3 : 0;
         if (P > 1 || g->emulate) reserve = std::min(32, std::max(2, reserve));
       }
-      MG_RC(smnngp_stage_update_f64(s, arows, db, pfull + na * db, db, g->a + ls * g->ld + c1 + na, g->ld, m,
-                                    n - c1 - na, w, 1, db, P, shiftc - na, reserve));
+      MG_RC(smnngp_stage_update2_f64(s, arows, db, pfull + na * db, db, g->a + ls * g->ld + c1 + na, g->ld, m,
+                                     n - c1 - na, w, 1, db, P, shiftc - na, alt, reserve));
     }
     mark(g, s, (int)p, 6);                                           // update_b
     ls = ls2;
@@ -723,7 +791,8 @@ int smnngp_predict_mg_f64(smnngp_mg* g, void* stream, const double* X, const dou
     PeerSignal sg;
     signal_for(g, FLAG_Z, seq0 + 2, sg, zp, g->off_z);
     long long row = 0;                                               // index into the carried rows (global order)
-    for (long long b = g->rank; b < g->nblocks; b += g->P) {
+    for (long long LB = 0; g->blk(LB, g->rank) < g->nblocks; LB++) {
+      const long long b = g->blk(LB, g->rank);
       const long long g0 = b * db, g1 = g0 + g->block_rows(b);
       if (g1 <= n) continue;
       const long long j0 = std::max(g0, n), j1 = std::min(g1, n + C);   // right-hand sides in this block
@@ -748,7 +817,8 @@ int smnngp_predict_mg_f64(smnngp_mg* g, void* stream, const double* X, const dou
     PeerSignal sg;
     signal_for(g, FLAG_RES, seq0 + 3, sg, rp, g->off_res);
     long long row = 0;
-    for (long long b = g->rank; b < g->nblocks; b += g->P) {
+    for (long long LB = 0; g->blk(LB, g->rank) < g->nblocks; LB++) {
+      const long long b = g->blk(LB, g->rank);
       const long long g0 = b * db, g1 = g0 + g->block_rows(b);
       if (g1 <= n) continue;
       const long long first = std::max(g0, n);

@@ -83,17 +83,18 @@ int smnngp_stage_trsm_f64(void* stream, double* R, int64_t ldr, int64_t m, int64
   return SMNNGP_OK;
 }
 
-// C [M, N] -= A [M, K] * B [N, K]^T with the block-row-cyclic lower mask (cyc_db = 0: plain lower / no mask)
-int smnngp_stage_update_f64(void* stream, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+// C [M, N] -= A [M, K] * B [N, K]^T with the block-row-cyclic lower mask (cyc_db = 0: plain lower / no mask);
+// cyc_alt: extra column shift of the rows of odd local blocks (snake distribution, see GemmParams)
+int smnngp_stage_update2_f64(void* stream, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                             int64_t ldc, int64_t M, int64_t N, int64_t K, int lower, int64_t cyc_db, int64_t cyc_p,
-                            int64_t base_shift, int sm_reserve) {
+                            int64_t base_shift, int64_t cyc_alt, int sm_reserve) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Enter scope(s);
   if (!A || !B || !C || M < 0 || N < 0 || K <= 0) return SMNNGP_EINVAL;
   GemmParams u{};
   u.A = A; u.lda = lda; u.B = B; u.ldb = ldb; u.C = C; u.ldc = ldc;
   u.M = (int)M; u.N = (int)N; u.K = (int)K; u.lower = lower;
-  u.cyc_db = (int)cyc_db; u.cyc_p = (int)cyc_p; u.base_shift = (int)base_shift;
+  u.cyc_db = (int)cyc_db; u.cyc_p = (int)cyc_p; u.base_shift = (int)base_shift; u.cyc_alt = (int)cyc_alt;
   u.sm_reserve = sm_reserve > 0 ? sm_reserve : 0;
   const bool timed = instr().time_updates && K >= 256;      // outer trailing updates only
   if (timed) {
@@ -107,6 +108,12 @@ int smnngp_stage_update_f64(void* stream, const double* A, int64_t lda, const do
   cudaError_t e = launch_gemm_sub(s, u);
   if (timed) instr_end_update(s);
   return fail_stage(e);
+}
+
+int smnngp_stage_update_f64(void* stream, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                            int64_t ldc, int64_t M, int64_t N, int64_t K, int lower, int64_t cyc_db, int64_t cyc_p,
+                            int64_t base_shift, int sm_reserve) {
+  return smnngp_stage_update2_f64(stream, A, lda, B, ldb, C, ldc, M, N, K, lower, cyc_db, cyc_p, base_shift, 0, sm_reserve);
 }
 
 // predictive tail for carried rows: V [T, ldv] = K_td L^-T rows, Z [C, ldz] = (L^-1 Y)^T rows, ktt [T] prior variances

@@ -58,6 +58,7 @@ struct TmaShape {
   // of one long strip of a tile row whose B operand streams from DRAM again for every tile row.  Tile slots outside
   // the matrix or above the diagonal are skipped (producer and math warps decode alike).
   int super_rows;
+  int cyc_alt;          // block-row-cyclic mask, snake distribution: extra shift of the rows of odd local blocks
 };
 
 __host__ __device__ __forceinline__ long long tma_super_count_tiles(int M, int N, int lower, int sr) {
@@ -77,7 +78,9 @@ __host__ __device__ __forceinline__ long long tma_super_count_tiles(int M, int N
 // work of others late in the factorisation).
 __host__ __device__ __forceinline__ int tma_cyc_row_tiles(const TmaShape& sh, int ti, int ntn) {
   const int rl = (ti * TM_BM + TM_BM < sh.M ? ti * TM_BM + TM_BM : sh.M) - 1;
-  const long long lim = (long long)rl + sh.base_shift + (long long)(rl / sh.cyc_db) * (sh.cyc_p - 1) * sh.cyc_db;
+  const int lb = rl / sh.cyc_db;
+  const long long lim = (long long)rl + sh.base_shift + (long long)lb * (sh.cyc_p - 1) * sh.cyc_db +
+                        ((lb & 1) ? sh.cyc_alt : 0);
   if (lim < 0) return 0;
   const long long c = lim / TM_BN + 1;
   return c < ntn ? (int)c : ntn;

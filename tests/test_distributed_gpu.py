@@ -84,6 +84,32 @@ def test_two_rank_matches_oracle(n, db, exchange):
         assert info == 0 and abs(out[1] - ref) <= 1e-8 * abs(ref)
 
 
+@pytest.mark.parametrize("layout", ["snake_end", "snake", "cyclic"])
+@pytest.mark.parametrize("n,db", [(2900, 128), (3000, 256)])
+def test_two_rank_block_layouts(n, db, layout, monkeypatch):
+    """the three block -> rank maps of the C driver (csrc/multigpu.cu: plain cyclic, snake, end-aligned snake = default):
+    same loss on both ranks, equal to the oracle"""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("SMNNGP_MG_LAYOUT", layout)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + n % 100 + {"snake_end": 0, "snake": 7, "cyclic": 14}[layout]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, 8, db, q, "peer")) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = _ref(n, 8, "student_t")
+    for rank, out, info in res:
+        assert info == 0 and abs(out[1] - ref) <= 1e-8 * abs(ref)
+    assert res[0][1] == res[1][1]
+
+
 def test_emulated_rank_schedule_runs_on_one_gpu():
     """DistributedLML(emulate=(P, rank)): the timing dry-run of one rank of a P-rank job (peer-store exchange with
     every peer aliased to the local buffers) must run to completion and record a timeline; its numbers are not
