@@ -76,7 +76,7 @@ struct smnngp_mg {
   bool opened[MAX_PEERS] = {};
   unsigned long long seq_base = 0;
   cudaStream_t side = nullptr, poison_stream = nullptr;
-  cudaEvent_t ev_panel = nullptr, ev_a = nullptr, ev_fork = nullptr, ev_done = nullptr;
+  cudaEvent_t ev_panel = nullptr, ev_a = nullptr, ev_a0 = nullptr, ev_fork = nullptr, ev_done = nullptr;
   // tuning
   int sm_reserve_override = -1;
   double reserve_margin = 4.5;            // see factor_all: SMs left to the look-ahead chain = margin * 82.5 w / ncols + 3
@@ -285,7 +285,10 @@ __global__ void reduce_gather_kernel(const double* __restrict__ slots, int P, do
 
 // one panel on stream s: owner factors + publishes W, everybody solves + scatters, waits for the whole panel.
 // Returns this rank's rows below the diagonal block (local offset ls, count m).
-int panel_step(smnngp_mg* g, cudaStream_t s, long long p, int* info_dev, long long& ls, long long& m) {
+// rows_ready (optional): event after which ALL of this rank's rows of block column p are up to date; the owner's
+// diagonal block only needs its own rows, which the caller updates first (the stream already waited for them).
+int panel_step(smnngp_mg* g, cudaStream_t s, long long p, int* info_dev, long long& ls, long long& m,
+               cudaEvent_t rows_ready = nullptr) {
   const long long n = g->n, db = g->db;
   const int P = g->P;
   const long long c0 = p * db, c1 = std::min((p + 1) * db, n), w = c1 - c0;
@@ -313,6 +316,7 @@ int panel_step(smnngp_mg* g, cudaStream_t s, long long p, int* info_dev, long lo
     MG_CU(launch_assemble_inverse(s, blk, g->ld, (int)w, g->linv, outs, P, db, &sg));
   }
   mark(g, s, (int)p, 0);                                                          // diag
+  if (rows_ready != nullptr) MG_CU(cudaStreamWaitEvent(s, rows_ready, 0));
   if (!g->emulate || g->rank == own)
     MG_RC(smnngp_stage_wait_flags_f64(s, g->flags_local(), FLAG_W, 1, seq, g->timeout_s, info_dev));
   mark(g, s, (int)p, 1);                                                          // bcast
@@ -464,6 +468,7 @@ static int mg_create_impl(smnngp_mg** out, int rank, int world, int64_t n, int64
        cudaStreamCreateWithFlags(&g->poison_stream, cudaStreamNonBlocking) == cudaSuccess &&
        cudaEventCreateWithFlags(&g->ev_panel, cudaEventDisableTiming) == cudaSuccess &&
        cudaEventCreateWithFlags(&g->ev_a, cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&g->ev_a0, cudaEventDisableTiming) == cudaSuccess &&
        cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
        cudaEventCreateWithFlags(&g->ev_done, cudaEventDisableTiming) == cudaSuccess;
   if (!ok || cudaDeviceSynchronize() != cudaSuccess) {
@@ -598,7 +603,7 @@ int smnngp_mg_destroy(smnngp_mg* g) {
     if (p) cudaFree(p);
   if (g->counters) cudaFree(g->counters);
   if (g->info_tmp) cudaFree(g->info_tmp);
-  for (cudaEvent_t e : {g->ev_panel, g->ev_a, g->ev_fork, g->ev_done})
+  for (cudaEvent_t e : {g->ev_panel, g->ev_a, g->ev_a0, g->ev_fork, g->ev_done})
     if (e) cudaEventDestroy(e);
   if (g->side) cudaStreamDestroy(g->side);
   if (g->poison_stream) cudaStreamDestroy(g->poison_stream);
@@ -637,14 +642,27 @@ int factor_all(smnngp_mg* g, cudaStream_t s, const double* X, const double* y, c
     const long long shiftc = gb0 * db - c1;
     const long long na = std::min(db, n - c1);                     // next panel's block column first
     const long long alt = g->cyc_alt(gb0);
-    if (m > 0)
+    // The rank that factors the NEXT diagonal block updates that block's rows first and lets its chain start on them
+    // (ev_a0); the rest of its rows of the block column follow (ev_a), and its panel solve waits for those.
+    const bool own_next = g->owner(p + 1) == g->rank && gb0 == p + 1 && m > na;
+    cudaEvent_t rows_ready = nullptr;
+    if (own_next) {
+      MG_RC(smnngp_stage_update2_f64(s, arows, db, pfull, db, g->a + ls * g->ld + c1, g->ld, na, na, w, 1, db, P, shiftc,
+                                     alt, 0));
+      MG_CU(cudaEventRecord(g->ev_a0, s));
+      const long long gb1 = g->first_block_from(p + 2, g->rank);
+      MG_RC(smnngp_stage_update2_f64(s, arows + na * db, db, pfull, db, g->a + (ls + na) * g->ld + c1, g->ld, m - na, na,
+                                     w, 1, db, P, gb1 * db - c1, g->cyc_alt(gb1), 0));
+      rows_ready = g->ev_a;
+    } else if (m > 0) {
       MG_RC(smnngp_stage_update2_f64(s, arows, db, pfull, db, g->a + ls * g->ld + c1, g->ld, m, na, w, 1, db, P, shiftc,
                                      alt, 0));
+    }
     mark(g, s, (int)p, 5);                                           // update_a
     MG_CU(cudaEventRecord(g->ev_a, s));
-    MG_CU(cudaStreamWaitEvent(g->side, g->ev_a, 0));
+    MG_CU(cudaStreamWaitEvent(g->side, own_next ? g->ev_a0 : g->ev_a, 0));
     long long ls2 = 0, m2 = 0;
-    MG_RC(panel_step(g, g->side, p + 1, info_dev, ls2, m2));        // look-ahead: prepare panel p + 1
+    MG_RC(panel_step(g, g->side, p + 1, info_dev, ls2, m2, rows_ready));   // look-ahead: prepare panel p + 1
     MG_CU(cudaEventRecord(g->ev_panel, g->side));
     if (m > 0 && c1 + na < n) {                                     // the rest of the trailing matrix
       // SMs the fused panel solve needs to keep pace with this update: solve flops m w^2 at ~0.2 TF/s per SM against
