@@ -99,27 +99,54 @@ struct smnngp_mg {
   // mask), tabulated once at creation:
   //   cyclic    : b mod P                                   (distributed.BlockRowCyclic, the Python drivers)
   //   snake     : odd cycles of P blocks run backwards
-  //   snake_end : the same, but the cycles are aligned to the END of the matrix (default for P > 1).
+  //   snake_end : the same, but the cycles are aligned to the END of the matrix
+  //   auto      : (default for P > 1) plain cyclic or one of the 2P phases of the snake, whichever gives the busiest rank
+  //               the least modelled update work (rows x position^2 per block; the last block is usually short).
   // Why: in the lower-triangular update a block row's work grows with the square of its global index, so with the
   // plain order the rank at the end of each cycle always holds the widest block: 9 % more update flops than the mean
   // over a factorisation of 118 blocks on 8 ranks (max / mean 1.091), and every rank waits for it at every panel.
   // The snake pairs a wide block with a narrow one; aligning the cycles to the end puts the one incomplete cycle where
   // the blocks are cheap (max / mean 1.054 start-aligned, 1.0075 end-aligned at 118 blocks).
-  int layout = 0;                                   // 0 cyclic, 1 snake, 2 snake_end
+  int layout = 0;                                   // 0 cyclic, 1 snake (start-aligned), 2 snake_end, 3 auto
+  int snake_shift = -1;                             // phase of the snake actually used (-1: plain cyclic)
   std::vector<int> owner_tab;                       // [nblocks]
   std::vector<long long> lb_tab;                    // [nblocks] local block index on the owner
   std::vector<std::vector<long long>> blocks;       // [P][local blocks] global block ids, ascending
   long long even_off = 0, odd_off = 0;              // this rank's block(LB) formula (see above)
 
+  int snake_owner(long long b, int shift) const {
+    const long long x = b + shift;
+    const int j = (int)(x % P);
+    return ((x / P) & 1) ? P - 1 - j : j;
+  }
+  // model of the update work of block row b: rows x (global position)^2 (it is updated by b panels, each over ~b/2
+  // column blocks); returns the largest per-rank load of an assignment
+  double max_load(int shift) const {
+    std::vector<double> w((size_t)P, 0.0);
+    for (long long b = 0; b < nblocks; b++) {
+      const int r = shift < 0 ? (int)(b % P) : snake_owner(b, shift);
+      const double pos = ((double)b + 0.5) * (double)db;
+      w[r] += (double)block_rows(b) * pos * pos;
+    }
+    return *std::max_element(w.begin(), w.end());
+  }
   bool build_layout() {
+    // candidates: plain cyclic (shift -1) and the 2P phases of the snake; "auto" keeps the one whose busiest rank has
+    // the least modelled work (the same deterministic choice on every rank)
+    snake_shift = -1;
+    if (layout == 1) snake_shift = 0;
+    if (layout == 2) snake_shift = (int)((2 * P - nblocks % (2 * P)) % (2 * P));
+    if (layout == 3) {
+      double best = max_load(-1);
+      for (int sft = 0; sft < 2 * P; sft++) {
+        const double m = max_load(sft);
+        if (m < best * (1.0 - 1e-12)) { best = m; snake_shift = sft; }
+      }
+    }
     owner_tab.assign((size_t)nblocks, 0);
     lb_tab.assign((size_t)nblocks, 0);
     blocks.assign((size_t)P, {});
-    for (long long b = 0; b < nblocks; b++) {
-      const long long bb = layout == 2 ? nblocks - 1 - b : b;
-      const int j = (int)(bb % P);
-      owner_tab[b] = (layout != 0 && ((bb / P) & 1)) ? P - 1 - j : j;
-    }
+    for (long long b = 0; b < nblocks; b++) owner_tab[b] = snake_shift < 0 ? (int)(b % P) : snake_owner(b, snake_shift);
     for (long long b = 0; b < nblocks; b++) {
       lb_tab[b] = (long long)blocks[owner_tab[b]].size();
       blocks[owner_tab[b]].push_back(b);
@@ -414,10 +441,11 @@ static int mg_create_impl(smnngp_mg** out, int rank, int world, int64_t n, int64
   g->mtotal = n + g->extra;
   g->nblocks = cdiv(g->mtotal, g->db);
   {
-    const char* lay = getenv("SMNNGP_MG_LAYOUT");     // cyclic | snake | snake_end (default)
-    g->layout = world == 1 ? 0 : 2;
+    const char* lay = getenv("SMNNGP_MG_LAYOUT");     // cyclic | snake | snake_end | auto (default)
+    g->layout = world == 1 ? 0 : 3;
     if (lay != nullptr && strcmp(lay, "cyclic") == 0) g->layout = 0;
     if (lay != nullptr && strcmp(lay, "snake") == 0 && world > 1) g->layout = 1;
+    if (lay != nullptr && strcmp(lay, "snake_end") == 0 && world > 1) g->layout = 2;
     if (!g->build_layout()) {                         // (cannot happen for the three maps above)
       g->layout = 0;
       g->build_layout();

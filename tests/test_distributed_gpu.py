@@ -84,10 +84,10 @@ def test_two_rank_matches_oracle(n, db, exchange):
         assert info == 0 and abs(out[1] - ref) <= 1e-8 * abs(ref)
 
 
-@pytest.mark.parametrize("layout", ["snake_end", "snake", "cyclic"])
+@pytest.mark.parametrize("layout", ["auto", "snake_end", "snake", "cyclic"])
 @pytest.mark.parametrize("n,db", [(2900, 128), (3000, 256)])
 def test_two_rank_block_layouts(n, db, layout, monkeypatch):
-    """the three block -> rank maps of the C driver (csrc/multigpu.cu: plain cyclic, snake, end-aligned snake = default):
+    """the block -> rank maps of the C driver (csrc/multigpu.cu: plain cyclic, snake, end-aligned snake, auto = default):
     same loss on both ranks, equal to the oracle"""
     import torch
     import torch.multiprocessing as mp
@@ -96,7 +96,7 @@ def test_two_rank_block_layouts(n, db, layout, monkeypatch):
     monkeypatch.setenv("SMNNGP_MG_LAYOUT", layout)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29800 + n % 100 + {"snake_end": 0, "snake": 7, "cyclic": 14}[layout]
+    port = 29800 + n % 100 + {"snake_end": 0, "snake": 7, "cyclic": 14, "auto": 21}[layout]
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n, 8, db, q, "peer")) for r in range(2)]
     for p in procs:
         p.start()
