@@ -273,6 +273,11 @@ void smnngp_mg_set_reserve_margin(smnngp_mg* g, double margin); /* automatic res
 void smnngp_mg_timeline(smnngp_mg* g, int enable);            /* profiling: CUDA events at the stage boundaries */
 int smnngp_mg_timeline_read(smnngp_mg* g, int cap, int* panel_out, int* label_out, double* ms_out);
 const char* smnngp_mg_last_error(void);
+/* pure host function: the block -> rank map of a handle (layout: 0 cyclic, 1 snake, 2 snake_end, 3 auto = default;
+ * env SMNNGP_MG_LAYOUT overrides the default of smnngp_mg_create); owner_out [nblocks], load_out [world] (optional,
+ * modelled update work per rank); returns the number of distribution blocks */
+int64_t smnngp_mg_layout(int world, int64_t n, int64_t extra_rows, int64_t block, int layout, int* owner_out,
+                         double* load_out);
 int smnngp_lml_mg_f64(smnngp_mg* g, void* stream, const double* X, const double* y, int64_t D, int n_hidden, int act,
                       int arch, const double* hp_dev, int kind, int shift, double* out_dev, int* info_dev);
 /* NNGPKernel.predict (spax/kernels.py:29-32) / SPR.test_nll (spax/models.py:100-120, spax/likelihoods.py:30-33, :52-65)

@@ -40,7 +40,7 @@ EXPORTS = [
     "smnngp_stage_assemble_inverse_f64", "smnngp_stage_update2_f64", "smnngp_stage_trsm_scatter2_f64",
     "smnngp_mg_create", "smnngp_mg_destroy", "smnngp_mg_ipc_handle", "smnngp_mg_region", "smnngp_mg_connect_ipc",
     "smnngp_mg_connect_ptrs", "smnngp_mg_connect_emulated", "smnngp_mg_set_timeout", "smnngp_mg_set_sm_reserve", "smnngp_mg_set_reserve_margin",
-    "smnngp_mg_timeline", "smnngp_mg_timeline_read", "smnngp_mg_last_error", "smnngp_lml_mg_f64",
+    "smnngp_mg_timeline", "smnngp_mg_timeline_read", "smnngp_mg_last_error", "smnngp_mg_layout", "smnngp_lml_mg_f64",
     "smnngp_mg_create_predict", "smnngp_predict_mg_f64", "smnngp_test_nll_mg_f64",
 ]
 
@@ -237,6 +237,8 @@ def _declare(lib):
     lib.smnngp_mg_timeline.argtypes = [_vp, _i]
     lib.smnngp_mg_timeline_read.argtypes = [_vp, _i, _vp, _vp, _vp]
     lib.smnngp_mg_last_error.restype = C.c_char_p
+    lib.smnngp_mg_layout.restype = _i64
+    lib.smnngp_mg_layout.argtypes = [_i, _i64, _i64, _i64, _i, _vp, _vp]
     lib.smnngp_lml_mg_f64.argtypes = [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _i, _vp, _vp]
     lib.smnngp_mg_create_predict.argtypes = [_vp, _i, _i, _i64, _i64, _i64, _i64]
     lib.smnngp_predict_mg_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp]

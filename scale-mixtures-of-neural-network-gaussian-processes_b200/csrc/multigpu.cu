@@ -520,6 +520,33 @@ int smnngp_mg_create_predict(smnngp_mg** out, int rank, int world, int64_t n, in
   return mg_create_impl(out, rank, world, n, block, t, c);
 }
 
+// Pure host function (no CUDA call): the block -> rank map a handle with these parameters would use.
+// layout: 0 cyclic, 1 snake, 2 snake_end, 3 auto.  owner_out [nblocks]; returns nblocks (< 0: invalid argument).
+// load_out [world] (optional): modelled update work per rank (rows x position^2 per block), for tests / diagnostics.
+int64_t smnngp_mg_layout(int world, int64_t n, int64_t extra_rows, int64_t block, int layout, int* owner_out,
+                         double* load_out) {
+  if (world < 1 || world > MAX_PEERS || n <= 0 || extra_rows < 0 || block <= 0 || layout < 0 || layout > 3) return -1;
+  smnngp_mg g;
+  g.rank = 0; g.P = world; g.n = n; g.db = block; g.extra = extra_rows;
+  g.mtotal = n + extra_rows;
+  g.nblocks = cdiv(g.mtotal, g.db);
+  g.layout = world == 1 ? 0 : layout;
+  for (int r = 0; r < world; r++) {          // the formula check is per rank: run it for every rank
+    g.rank = r;
+    if (!g.build_layout()) return -2;
+  }
+  if (owner_out)
+    for (long long b = 0; b < g.nblocks; b++) owner_out[b] = g.owner_tab[b];
+  if (load_out) {
+    for (int r = 0; r < world; r++) load_out[r] = 0.0;
+    for (long long b = 0; b < g.nblocks; b++) {
+      const double pos = ((double)b + 0.5) * (double)g.db;
+      load_out[g.owner_tab[b]] += (double)g.block_rows(b) * pos * pos;
+    }
+  }
+  return g.nblocks;
+}
+
 int smnngp_mg_ipc_handle(smnngp_mg* g, unsigned char* handle_out64) {
   if (!g || !handle_out64) return mg_fail(SMNNGP_EINVAL, "smnngp_mg_ipc_handle: invalid argument");
   memcpy(handle_out64, g->handle, 64);

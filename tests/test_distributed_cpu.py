@@ -214,3 +214,33 @@ def test_eps_sweep_replicas(world):
         for eps, (m, v, ld, qd, info) in zip(eps_list, res):
             assert m == [k * eps for k in range(5)] and v == [k + eps for k in range(5)]
             assert ld == 10.0 * eps and qd == 100.0 * eps and info == (0 if eps < 1.0 else 7)
+
+
+@pytest.mark.parametrize("world,n,block", [(8, 60000, 512), (4, 60000, 512), (2, 60000, 512), (8, 150000, 512),
+                                           (8, 20000, 256), (3, 5000, 128), (2, 700, 128)])
+def test_c_driver_block_layouts(world, n, block):
+    """host logic of csrc/multigpu.cu (no GPU needed): every block -> rank map gives each rank blocks of the form
+    LB * P + (LB odd ? odd_off : even_off) - the property the scatter epilogue and the update mask rely on - and the
+    default (auto) never loads the busiest rank more than the plain cyclic map does"""
+    import ctypes as C
+    import smnngp_b200 as sm
+    lib = sm._lib.load()
+    nb = -(-(n + 1) // block)
+    res = {}
+    for layout in (0, 1, 2, 3):
+        owner = (C.c_int * nb)()
+        load = (C.c_double * world)()
+        assert lib.smnngp_mg_layout(world, n, 1, block, layout, owner, load) == nb
+        owner = list(owner)
+        assert set(owner) <= set(range(world))
+        for r in range(world):
+            mine = [b for b in range(nb) if owner[b] == r]
+            if len(mine) > 1:
+                even, odd = mine[0], mine[1] - world
+                assert all(b == lb * world + (odd if lb & 1 else even) for lb, b in enumerate(mine))
+            # one block per cycle of `world` consecutive blocks (so local block index = position in the list)
+            assert all(mine[i + 1] - mine[i] < 2 * world for i in range(len(mine) - 1))
+        res[layout] = max(load) / (sum(load) / world)
+    assert res[3] <= res[0] + 1e-12 and res[3] <= res[1] + 1e-12 and res[3] <= res[2] + 1e-12
+    if world == 8 and n == 60000:
+        assert res[0] > 1.08 and res[3] < 1.03          # 8.6 % -> 2.5 % over the mean (profiles/r02_layouts_8gpu.txt)
