@@ -287,6 +287,16 @@ int smnngp_lml_mg_f64(smnngp_mg* g, void* stream, const double* X, const double*
  * test_nll: g_pred built with c = 1, g_lik a plain smnngp_mg_create handle of the same n / block / group (second
  * factorisation K + 1e-6 (a/b) I of the Student-t likelihood; may be NULL for kind = gauss) -> nll_out_dev [1]. */
 int smnngp_mg_create_predict(smnngp_mg** out, int rank, int world, int64_t n, int64_t t, int64_t c, int64_t block);
+/* SPR.loss AND d loss / d {w_std, b_std, last_w_std, eps, alpha, beta} on the handle group - the value / gradient pair
+ * objax.GradValues(model.loss, model.vars()) produces in the reference's train step (experiments/regression/train.py:
+ * 62-66; the softplus chain rule is the caller's, as for smnngp_lml_grad_f64).  smnngp_mg_create_grad: the N identity
+ * rows ride through the distributed factorisation (-> U = L^-T), U is all-gathered over NVLink (every rank needs
+ * 8 N^2 bytes for it), every rank contracts one row strip of A^-1 = U U^T with dK/dtheta.  out_dev[4] as
+ * smnngp_lml_mg_f64, grad_dev[6], identical on every rank. */
+int smnngp_mg_create_grad(smnngp_mg** out, int rank, int world, int64_t n, int64_t block);
+int smnngp_lml_grad_mg_f64(smnngp_mg* g, void* stream, const double* X, const double* y, int64_t D, int n_hidden,
+                           int act, int arch, const double* hp_dev, int kind, double* out_dev, double* grad_dev,
+                           int* info_dev);
 int smnngp_predict_mg_f64(smnngp_mg* g, void* stream, const double* X, const double* Y, const double* Xt, int64_t D,
                           int n_hidden, int act, int arch, const double* hp_dev, int shift, double* mean_out,
                           double* var_out, int* info_dev);

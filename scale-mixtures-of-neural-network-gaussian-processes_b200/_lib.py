@@ -42,6 +42,7 @@ EXPORTS = [
     "smnngp_mg_connect_ptrs", "smnngp_mg_connect_emulated", "smnngp_mg_set_timeout", "smnngp_mg_set_sm_reserve", "smnngp_mg_set_reserve_margin",
     "smnngp_mg_timeline", "smnngp_mg_timeline_read", "smnngp_mg_last_error", "smnngp_mg_layout", "smnngp_lml_mg_f64",
     "smnngp_mg_create_predict", "smnngp_predict_mg_f64", "smnngp_test_nll_mg_f64",
+    "smnngp_mg_create_grad", "smnngp_lml_grad_mg_f64",
 ]
 
 
@@ -241,6 +242,8 @@ def _declare(lib):
     lib.smnngp_mg_layout.argtypes = [_i, _i64, _i64, _i64, _i, _vp, _vp]
     lib.smnngp_lml_mg_f64.argtypes = [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _i, _vp, _vp]
     lib.smnngp_mg_create_predict.argtypes = [_vp, _i, _i, _i64, _i64, _i64, _i64]
+    lib.smnngp_mg_create_grad.argtypes = [_vp, _i, _i, _i64, _i64]
+    lib.smnngp_lml_grad_mg_f64.argtypes = [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp]
     lib.smnngp_predict_mg_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp]
     lib.smnngp_test_nll_mg_f64.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _d, _d, _vp,
                                            _vp, _vp, _vp]

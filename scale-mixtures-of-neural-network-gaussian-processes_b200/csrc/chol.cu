@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_BLOCKS) gemm_kernel(con
     }
   }
   double acc[MI][NI][2];
-  const int k0 = p.k_from_row ? r0 : 0;        // r0 is a multiple of 128: alignment of the operands is kept
+  const int k0 = p.k_from_row ? p.k_row0 + r0 : 0;   // multiples of 64: alignment of the operands is kept
   gemm_mainloop<Cfg, ALIGN16>(acc, p.A + (long long)r0 * p.lda + k0, p.lda, min(Cfg::BM, p.M - r0),
                               p.B + (long long)c0 * p.ldb + k0, p.ldb, min(Cfg::BN, p.N - c0), p.K - k0, smem);
   gemm_epilogue<EPI>(p, acc, r0, c0, Cfg::BM, Cfg::BN, rbase, cbase);
@@ -138,6 +138,7 @@ cudaError_t launch_gemm_tma(cudaStream_t s, const GemmParams& p) {
   TmaShape sh{p.M, p.N, p.K, tri, count_tiles<TileTma>(p.M, p.N, tri), p.lower ? p.cyc_db : 0, p.cyc_p, p.base_shift,
               p.k_from_row, p.k_upto_col};
   sh.cyc_alt = p.lower ? p.cyc_alt : 0;
+  sh.k_row0 = p.k_row0;
   if (sh.cyc_db != 0) sh.tiles = tma_cyc_count_tiles(sh);       // active tiles only
   int sms = device_sm_count() - p.sm_reserve;
   if (sms < 8) sms = 8;

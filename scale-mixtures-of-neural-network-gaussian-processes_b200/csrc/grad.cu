@@ -113,12 +113,16 @@ struct GradParams {
   const double* quad;     // device: y^T A^-1 y
   int kind;
   double* partial;        // [slots][4]: sum G dK/dw, sum G dK/db, sum G K, tr G
+  // row strip (multi-GPU): tile rows are local to the strip, g.N = rows of the strip, Winv = the strip of A^-1;
+  // global row = row0 + local row; n_total = order of the whole matrix (0: not a strip, g.N)
+  int row0, n_total;
 };
 
 __device__ __forceinline__ double grad_gamma(const GradParams& p) {
   if (p.kind != KIND_STUDENT_T) return 1.0;
   const double a = p.g.hp[HP_ALPHA], b = p.g.hp[HP_BETA];
-  return (2.0 * a + (double)p.g.N) / ((2.0 * a + (*p.quad) * a / b) * (b / a));
+  const double n = (double)(p.n_total > 0 ? p.n_total : p.g.N);
+  return (2.0 * a + n) / ((2.0 * a + (*p.quad) * a / b) * (b / a));
 }
 
 // one warp's 64 x 32 part of a tile: returns the four partial sums of this THREAD in sums[]
@@ -137,7 +141,9 @@ __device__ __forceinline__ void grad_epilogue(const GradParams& p, double (&acc)
   const double* __restrict__ t2 = p.tab3 + 2 * p.plane;
   const long long tl = p.g.tab_ld1;
   sums[0] = sums[1] = sums[2] = sums[3] = 0.0;
-  if (cbase > rbase + (MI - 1) * 8 || rbase >= N) return;        // nothing of this thread lies in the lower triangle
+  const int row0 = p.row0;                                       // global row of the strip's first row (0: whole matrix)
+  if (cbase > row0 + rbase + (MI - 1) * 8 || rbase >= N) return; // nothing of this thread lies in the lower triangle
+  const int ncols = p.g.M;
 
   int cc[NI][2];
   double al_c[NI][2];
@@ -145,7 +151,7 @@ __device__ __forceinline__ void grad_epilogue(const GradParams& p, double (&acc)
   for (int ni = 0; ni < NI; ni++)
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      cc[ni][e] = min(cbase + ni * 8 + e, N - 1);
+      cc[ni][e] = min(cbase + ni * 8 + e, ncols - 1);
       al_c[ni][e] = p.alpha[cc[ni][e]];
     }
 
@@ -153,8 +159,9 @@ __device__ __forceinline__ void grad_epilogue(const GradParams& p, double (&acc)
   // through the registers - the fully unrolled version was ~29k instructions and ran at the instruction-fetch rate.
 #pragma unroll 1
   for (int it = 0; it < MI; it++) {
-    const int r = rbase + it * 8;
-    if (r < N && cbase <= r) {
+    const int rl = rbase + it * 8;                               // row inside the strip
+    const int r = row0 + rl;                                       // global row
+    if (rl < N && cbase <= r) {
       double k[NI][2], dw[NI][2], db[NI][2];
 #pragma unroll
       for (int ni = 0; ni < NI; ni++)
@@ -193,7 +200,7 @@ __device__ __forceinline__ void grad_epilogue(const GradParams& p, double (&acc)
           }
       }
       const double al_r = p.alpha[r];
-      const double* __restrict__ wrow = p.Winv + (long long)r * p.ldw;
+      const double* __restrict__ wrow = p.Winv + (long long)rl * p.ldw;
 #pragma unroll
       for (int ni = 0; ni < NI; ni++)
 #pragma unroll
@@ -376,6 +383,13 @@ cudaError_t launch_set_identity(cudaStream_t s, double* A, long long lda, long l
   return cudaGetLastError();
 }
 
+cudaError_t launch_set_ones_diag(cudaStream_t s, double* A, long long lda, long long N) {
+  if (N <= 0) return cudaSuccess;
+  set_identity_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(A, lda, N);
+  instr().launches++;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_upper_gemv(cudaStream_t s, const double* U, long long ldu, const double* z, long long N,
                               double* out) {
   if (N <= 0) return cudaSuccess;
@@ -410,6 +424,62 @@ cudaError_t launch_grad_gram(cudaStream_t s, const double* X, long long N, long 
   }
   const bool a16 = (D % 2 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
   return a16 ? launch_grad_fallback<true>(s, p) : launch_grad_fallback<false>(s, p);
+}
+
+cudaError_t launch_grad_gram_strip(cudaStream_t s, const double* X, long long N, long long D, long long row0,
+                                   long long rows, int n_hidden, int act, int arch, const double* hp, const double* tab3,
+                                   long long tab_ld, const double* Winv_strip, long long ldw, const double* alpha,
+                                   const double* quad, int kind, double* partial, long long slots) {
+  cudaError_t e = cudaMemsetAsync(partial, 0, (size_t)slots * 4 * sizeof(double), s);
+  if (e != cudaSuccess || rows <= 0) return e;
+  if (!(tile_variant() == 0 && tma_operand_ok(X, D)) || (row0 % TM_BM) != 0) return cudaErrorInvalidValue;
+  const long long ncols = row0 + rows;
+  GradParams p{};
+  p.g.X1 = X + row0 * D; p.g.X2 = X; p.g.ld1 = D; p.g.ld2 = D; p.g.N = (int)rows; p.g.M = (int)ncols; p.g.D = (int)D;
+  p.g.tab1 = tab3; p.g.tab2 = tab3; p.g.tab_ld1 = tab_ld; p.g.tab_ld2 = tab_ld;
+  p.g.n_hidden = n_hidden; p.g.act = act; p.g.arch = arch; p.g.hp = hp; p.g.symmetric = 1;
+  p.tab3 = tab3;
+  const int n_act = n_act_applications(n_hidden, arch);
+  p.plane = (long long)(n_act > 0 ? n_act : 1) * tab_ld;
+  p.Winv = Winv_strip; p.ldw = ldw; p.alpha = alpha; p.quad = quad; p.kind = kind; p.partial = partial;
+  p.row0 = (int)row0; p.n_total = (int)N;
+  CUtensorMap ma, mb;
+  if (!make_tmap(&ma, X + row0 * D, rows, D, D, TM_BM) || !make_tmap(&mb, X, ncols, D, D, TM_BN))
+    return cudaErrorInvalidValue;
+  // lower part of the strip: local row r may touch columns <= row0 + r (the shifted-diagonal mask of the update kernel)
+  TmaShape sh{(int)rows, (int)ncols, (int)D, 0, 0, 1 << 30, 1, (int)row0, 0};
+  sh.tiles = tma_cyc_count_tiles(sh);
+  e = act == ACT_RELU ? launch_tma_gemm<EpiGradTma<ACT_RELU>>(s, ma, mb, sh, p, device_sm_count())
+                      : launch_tma_gemm<EpiGradTma<ACT_ERF>>(s, ma, mb, sh, p, device_sm_count());
+  instr().launches++;
+  return e;
+}
+
+namespace {
+__global__ void __launch_bounds__(1024) sum_slots_kernel(const double* __restrict__ partial, long long slots,
+                                                         double* __restrict__ out4) {
+  __shared__ double red[4][1024];
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long i = threadIdx.x; i < slots; i += 1024)
+#pragma unroll
+    for (int q = 0; q < 4; q++) s[q] += partial[i * 4 + q];
+#pragma unroll
+  for (int q = 0; q < 4; q++) red[q][threadIdx.x] = s[q];
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o)
+#pragma unroll
+      for (int q = 0; q < 4; q++) red[q][threadIdx.x] += red[q][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) out4[threadIdx.x] = red[threadIdx.x][0];
+}
+}  // namespace
+
+cudaError_t launch_sum_slots(cudaStream_t s, const double* partial, long long slots, double* out4) {
+  sum_slots_kernel<<<1, 1024, 0, s>>>(partial, slots, out4);
+  instr().launches++;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_grad_finalize(cudaStream_t s, const double* partial, long long slots, const double* hp,

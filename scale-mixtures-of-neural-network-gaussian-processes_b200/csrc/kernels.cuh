@@ -55,6 +55,7 @@ struct GemmParams {
   // snake (boustrophedon) block distribution: consecutive local blocks are alternately (P - 1 - 2 rank) blocks
   // closer / further apart than P; rows of ODD local blocks (counted from the first row of C) get this extra shift
   int cyc_alt;
+  int k_row0;         // with k_from_row: global index of C's first row when C is a row strip of a larger product
 };
 
 // largest active column of local row r (rows are non-decreasing in this limit)
@@ -141,6 +142,8 @@ cudaError_t launch_qtable_dual(cudaStream_t s, const double* X, long long ldx, i
                                int arch, const double* hp, double* tab3, long long tab_ld);
 // A [N, lda] <- identity (zero fill + ones)
 cudaError_t launch_set_identity(cudaStream_t s, double* A, long long lda, long long N);
+// A[i, i] = 1 for i < N (no zero fill)
+cudaError_t launch_set_ones_diag(cudaStream_t s, double* A, long long lda, long long N);
 // out_i = sum_{k >= i} U[i,k] z[k]
 cudaError_t launch_upper_gemv(cudaStream_t s, const double* U, long long ldu, const double* z, long long N,
                               double* out);
@@ -150,6 +153,14 @@ cudaError_t launch_grad_gram(cudaStream_t s, const double* X, long long N, long 
                              int arch, const double* hp, const double* tab3, long long tab_ld, const double* Winv,
                              long long ldw, const double* alpha, const double* quad, int kind, double* partial,
                              long long slots);
+// the same contraction restricted to the row strip [row0, row0 + rows) x [0, row0 + rows) of the lower triangle
+// (multi-GPU gradient: every rank takes one strip): Winv [rows, ldw] = that strip of A^-1, everything else global
+cudaError_t launch_grad_gram_strip(cudaStream_t s, const double* X, long long N, long long D, long long row0,
+                                   long long rows, int n_hidden, int act, int arch, const double* hp, const double* tab3,
+                                   long long tab_ld, const double* Winv_strip, long long ldw, const double* alpha,
+                                   const double* quad, int kind, double* partial, long long slots);
+// out4 = fixed-order sum of partial [slots][4]
+cudaError_t launch_sum_slots(cudaStream_t s, const double* partial, long long slots, double* out4);
 cudaError_t launch_grad_finalize(cudaStream_t s, const double* partial, long long slots, const double* hp,
                                  const double* quad, int kind, long long N, const int* info, double* grad);
 

@@ -25,6 +25,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -40,7 +41,7 @@ namespace {
 // flag words: 0: W ready; 8..15: panel ready (per source rank); 16..23: reduce slot ready; 24..31: right-hand-side
 // rows (L^-1 Y)^T ready; 32..39: predictive results ready
 constexpr int FLAG_WORDS = 64;
-constexpr int FLAG_W = 0, FLAG_PANEL = 8, FLAG_REDUCE = 16, FLAG_Z = 24, FLAG_RES = 32;
+constexpr int FLAG_W = 0, FLAG_PANEL = 8, FLAG_REDUCE = 16, FLAG_Z = 24, FLAG_RES = 32, FLAG_GRAD = 40;
 constexpr int REDUCE_DOUBLES = 4;  // per source rank: sum log L_ii, ||z||^2, info (as double), pad
 
 inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
@@ -55,6 +56,12 @@ struct smnngp_mg {
   // predictive handle: rows n .. n+c-1 = Y^T (right-hand sides), rows n+c .. n+c+t-1 = test-train cross-Gram;
   // LML handle: t = 0, c = 1 (the single carried row y^T)
   long long t = 0, c = 1;
+  // gradient handle (smnngp_mg_create_grad): t = n "test rows" that start as the IDENTITY and come out as U = L^-T
+  bool grad = false;
+  double *tab3 = nullptr, *alpha = nullptr, *strip = nullptr, *partial = nullptr, *psum = nullptr;
+  size_t tab3_doubles = 0;
+  long long strip_r0 = 0, strip_r1 = 0, strip_ld = 0, slots = 0;
+  size_t off_u = 0, off_gslots = 0;       // peer region: full U [n, ld] (all-gathered), per-rank gradient partial sums
   long long extra_lo = 0, n_carried = 0;  // local storage keeps global order: the carried rows are its tail
   bool emulate = false, connected = false;
   std::atomic<bool> dead{false};
@@ -194,6 +201,18 @@ struct smnngp_mg {
     const auto& v = blocks[owner_tab[gb0]];
     const long long LB0 = lb_tab[gb0];
     return LB0 + 1 < (long long)v.size() ? (v[LB0 + 1] - gb0 - P) * db : 0;
+  }
+  // gradient handle: identity row i is still e_i (zero in every column < i) until the panel that contains column i,
+  // so while panel [c0, c1) is processed only local rows with global index < n + c + c1 take part
+  long long active_prefix(long long c1) const {
+    const long long limit = grad ? n + c + c1 : mtotal;
+    long long cnt = 0;
+    for (long long b : blocks[rank]) {
+      const long long g0 = b * db, g1 = g0 + block_rows(b);
+      if (g0 >= limit) break;
+      cnt += std::min(g1, limit) - g0;
+    }
+    return cnt;
   }
   unsigned long long* flags_local() const { return reinterpret_cast<unsigned long long*>(region + off_flags); }
   double* w_local() const { return reinterpret_cast<double*>(region + off_w); }
@@ -353,6 +372,7 @@ int panel_step(smnngp_mg* g, cudaStream_t s, long long p, int* info_dev, long lo
   } else {
     g->rows_from_block(p + 1, g->rank, ls, m);
   }
+  if (g->grad) m = std::max<long long>(0, std::min(m, g->active_prefix(c1) - ls));
   double* ploc = g->ploc[p & 1];
   MG_RC(smnngp_stage_trsm_scatter2_f64(s, g->a + ls * g->ld + c0, g->ld, m, w, g->w_local(), db, ploc, db, panel_ptrs, P,
                                        g->rank, db, ls, c1, n, db, flag_ptrs, FLAG_PANEL + g->rank, seq,
@@ -419,6 +439,11 @@ int build_gram(smnngp_mg* g, cudaStream_t s, const double* X, const double* y, c
       if (xt != nullptr && t1 > t0)
         MG_RC(smnngp_stage_gram_f64(s, xt + t0 * D, t1 - t0, X, n, D, nh, act, arch, hp, g->tab_t + t0, g->t, g->tab, n,
                                     g->scal, SHIFT_NONE, 0, g->a + (lo + (n + g->c + t0 - g0)) * g->ld, g->ld));
+      if (g->grad && t1 > t0) {                                            // identity rows t0 .. t1-1
+        double* rows = g->a + (lo + (n + g->c + t0 - g0)) * g->ld;
+        MG_CU(cudaMemsetAsync(rows, 0, (size_t)(t1 - t0) * g->ld * 8, s));
+        MG_CU(launch_set_ones_diag(s, rows + t0, g->ld, t1 - t0));
+      }
     }
   }
   return SMNNGP_OK;
@@ -430,12 +455,13 @@ extern "C" {
 
 const char* smnngp_mg_last_error(void) { return g_mg_err; }
 
-static int mg_create_impl(smnngp_mg** out, int rank, int world, int64_t n, int64_t block, int64_t t, int64_t c) {
+static int mg_create_impl(smnngp_mg** out, int rank, int world, int64_t n, int64_t block, int64_t t, int64_t c,
+                          bool grad = false) {
   if (!out || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || n <= 0 || block <= 0 || block % PB != 0 ||
       block > LINV_BLOCKS * PB || t < 0 || c < 1 || n + t + c > INT32_MAX)
     return mg_fail(SMNNGP_EINVAL, "smnngp_mg_create: invalid argument");
   smnngp_mg* g = new smnngp_mg();
-  g->rank = rank; g->P = world; g->n = n; g->db = block; g->t = t; g->c = c;
+  g->rank = rank; g->P = world; g->n = n; g->db = block; g->t = t; g->c = c; g->grad = grad;
   g->extra = t + c;
   cudaGetDevice(&g->device);
   g->mtotal = n + g->extra;
@@ -466,7 +492,9 @@ static int mg_create_impl(smnngp_mg** out, int rank, int world, int64_t n, int64
   g->off_reduce = g->off_panel + 3 * g->slot_bytes;
   g->off_z = g->off_reduce + (size_t)MAX_PEERS * REDUCE_DOUBLES * 8;
   g->off_res = g->off_z + (t > 0 ? (size_t)c * n * 8 : 0);
-  g->region_bytes = g->off_res + (t > 0 ? (size_t)t * (c + 1) * 8 : 0) + 256;
+  g->off_gslots = g->off_res + ((t > 0 && !grad) ? (size_t)t * (c + 1) * 8 : 0);
+  g->off_u = (g->off_gslots + (size_t)MAX_PEERS * 4 * 8 + 255) & ~(size_t)255;
+  g->region_bytes = g->off_u + (grad ? (size_t)n * g->ld * 8 : 0) + 256;
   void* reg = nullptr;
   if (smnngp_peer_alloc(g->region_bytes, &reg, g->handle) != SMNNGP_OK) {
     delete g;
@@ -487,9 +515,27 @@ static int mg_create_impl(smnngp_mg** out, int rank, int world, int64_t n, int64
             cudaMalloc(&g->info_tmp, sizeof(int)) == cudaSuccess &&
             cudaMemset(g->counters, 0, 8 * sizeof(unsigned int)) == cudaSuccess &&
             cudaMemset(g->carried, 0, (size_t)crow * g->ld * 8) == cudaSuccess;
-  if (ok && t > 0)
+  if (ok && t > 0 && !grad)
     ok = cudaMalloc(&g->q_t, (size_t)t * 8) == cudaSuccess &&
          cudaMalloc(&g->res_tmp, (size_t)t * (c + 1) * 8) == cudaSuccess;
+  if (ok && grad) {
+    // every rank contracts one row strip [r0, r1) x [0, r1) of the lower triangle of A^-1 with dK/dtheta; strips of
+    // equal area: r ~ N sqrt(k / P), aligned to the 128-row tile
+    auto cut = [&](int k) {
+      long long r = (long long)(std::sqrt((double)k / (double)world) * (double)n / 128.0 + 0.5) * 128;
+      return k >= world ? (long long)n : std::min<long long>(r, n);
+    };
+    g->strip_r0 = cut(rank);
+    g->strip_r1 = cut(rank + 1);
+    g->strip_ld = cdiv(std::max<long long>(g->strip_r1, 1), 16) * 16;
+    g->slots = grad_partial_slots(n);
+    const long long srows = std::max<long long>(g->strip_r1 - g->strip_r0, 1);
+    ok = cudaMalloc(&g->alpha, (size_t)n * 8) == cudaSuccess &&
+         cudaMalloc(&g->strip, (size_t)srows * g->strip_ld * 8) == cudaSuccess &&
+         cudaMalloc(&g->partial, (size_t)g->slots * 4 * 8) == cudaSuccess &&
+         cudaMalloc(&g->psum, 4 * 8) == cudaSuccess &&
+         cudaMemset(g->region + g->off_u, 0, (size_t)n * g->ld * 8) == cudaSuccess;
+  }
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
   ok = ok && cudaStreamCreateWithPriority(&g->side, cudaStreamNonBlocking, hi) == cudaSuccess &&
@@ -515,6 +561,11 @@ int smnngp_mg_create(smnngp_mg** out, int rank, int world, int64_t n, int64_t bl
 }
 // handle for smnngp_predict_mg_f64 / smnngp_test_nll_mg_f64: T test points and C right-hand sides ride along as extra
 // global rows of the same layout
+// handle for smnngp_lml_grad_mg_f64: the N rows of the identity ride through the factorisation (they come out as
+// U = L^-T, all-gathered afterwards: every rank needs 8 N^2 bytes for it)
+int smnngp_mg_create_grad(smnngp_mg** out, int rank, int world, int64_t n, int64_t block) {
+  return mg_create_impl(out, rank, world, n, block, n, 1, true);
+}
 int smnngp_mg_create_predict(smnngp_mg** out, int rank, int world, int64_t n, int64_t t, int64_t c, int64_t block) {
   if (t <= 0) return mg_fail(SMNNGP_EINVAL, "smnngp_mg_create_predict: t must be positive");
   return mg_create_impl(out, rank, world, n, block, t, c);
@@ -654,7 +705,7 @@ int smnngp_mg_destroy(smnngp_mg* g) {
     if (g->opened[r]) smnngp_peer_close(g->bases[r]);
   if (g->region) smnngp_peer_free(g->region);
   for (double* p : {g->a, g->tab, g->q, g->scal, g->linv, g->carried, g->sums, g->ploc[0], g->ploc[1], g->tab_t, g->q_t,
-                    g->res_tmp})
+                    g->res_tmp, g->tab3, g->alpha, g->strip, g->partial, g->psum})
     if (p) cudaFree(p);
   if (g->counters) cudaFree(g->counters);
   if (g->info_tmp) cudaFree(g->info_tmp);
@@ -680,6 +731,8 @@ int factor_all(smnngp_mg* g, cudaStream_t s, const double* X, const double* y, c
   MG_CU(cudaMemsetAsync(info_dev, 0, sizeof(int), s));
   MG_CU(cudaMemsetAsync(g->sums, 0, 2 * sizeof(double), s));
   MG_RC(build_gram(g, s, X, y, xt, D, nh, act, arch, hp_dev, shift));
+  if (g->grad)     // rows that never become active keep their zeros (U is upper triangular)
+    MG_CU(cudaMemsetAsync(g->carried, 0, (size_t)std::max<long long>(g->n_carried, 1) * g->ld * 8, s));
   const long long npanels = cdiv(n, db);
   MG_CU(cudaEventRecord(g->ev_fork, s));
   MG_CU(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
@@ -834,6 +887,120 @@ int smnngp_lml_mg_f64(smnngp_mg* g, void* stream, const double* X, const double*
   MG_RC(reduce_all(g, s, g->seq_base + (unsigned long long)npanels + 1, info_dev));
   MG_CU(launch_lml_finalize(s, g->scal, hp_dev, kind, n, info_dev, out_dev));
   g->seq_base += (unsigned long long)npanels + 4;
+  arm_watchdog(g, s, info_dev);
+  return SMNNGP_OK;
+}
+
+// SPR.loss AND its gradient w.r.t. {w_std, b_std, last_w_std, eps, alpha, beta} - what objax.GradValues(model.loss, vars)
+// computes in the reference's training step (experiments/regression/train.py:62-66) - on the ranks of the handle group.
+// out_dev[4] as smnngp_lml_mg_f64, grad_dev[6] = d loss / d hp, identical on every rank.
+//   1. factorisation with the N identity rows carried along (rows of U = L^-T, block-cyclic like everything else; a
+//      row only takes part once its column has been reached: N^3/3 extra flop, not N^3);
+//   2. z = L^-1 y is stored to every rank; every rank's U rows are copied to every rank (copy engines over NVLink,
+//      right of the diagonal only); a = A^-1 y = U z on every rank;
+//   3. every rank forms ONE row strip of A^-1 = U U^T (equal-area strips of the lower triangle, contraction from the
+//      diagonal on) and contracts it with dK/dtheta in the dual Gram pass of grad.cu restricted to that strip;
+//   4. the four partial sums per rank go through peer slots, are added in rank order and finalised (closed forms for
+//      the inverse-gamma parameters).
+int smnngp_lml_grad_mg_f64(smnngp_mg* g, void* stream, const double* X, const double* y, int64_t D, int n_hidden,
+                           int act, int arch, const double* hp_dev, int kind, double* out_dev, double* grad_dev,
+                           int* info_dev) {
+  if (!g || !X || !y || !hp_dev || !out_dev || !grad_dev || !info_dev || D <= 0 || !valid_stack_mg(n_hidden, act, arch) ||
+      (kind != KIND_GAUSS && kind != KIND_STUDENT_T) || !g->grad)
+    return mg_fail(SMNNGP_EINVAL, "smnngp_lml_grad_mg_f64: invalid argument (needs a handle from smnngp_mg_create_grad)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Enter scope(s);
+  MG_RC(check_call(g, s, scope, "smnngp_lml_grad_mg_f64"));
+  const long long n = g->n, db = g->db, ld = g->ld, npanels = cdiv(n, db);
+  const int P = g->P;
+  const unsigned long long seq0 = g->seq_base + (unsigned long long)npanels;
+  const int n_act = std::max(n_act_applications(n_hidden, arch), 1);
+  if ((size_t)3 * n_act * n > g->tab3_doubles) {
+    if (g->tab3) cudaFree(g->tab3);
+    g->tab3 = nullptr;
+    MG_CU(cudaMalloc(&g->tab3, (size_t)3 * n_act * n * 8));
+    g->tab3_doubles = (size_t)3 * n_act * n;
+  }
+  // ---- 1. value: factorisation with y^T and the identity rows carried ----
+  MG_RC(factor_all(g, s, X, y, nullptr, D, n_hidden, act, arch, hp_dev, SMNNGP_SHIFT_EPS_ABS, info_dev));
+  if (g->owner(n / db) == g->rank) MG_CU(launch_sumsq(s, g->carried, n, g->sums + 1));      // carried row 0 = z^T
+  MG_RC(reduce_all(g, s, seq0 + 1, info_dev));
+  MG_CU(launch_lml_finalize(s, g->scal, hp_dev, kind, n, info_dev, out_dev));
+  MG_CU(launch_qtable_dual(s, X, D, (int)n, (int)D, n_hidden, act, arch, hp_dev, g->tab3, n));
+  double* zloc = reinterpret_cast<double*>(g->region + g->off_z);
+  double* Uloc = reinterpret_cast<double*>(g->region + g->off_u);
+  // ---- 2. z and U to every rank ----
+  {
+    void* zp[MAX_PEERS];
+    void* up[MAX_PEERS];
+    PeerSignal sg;
+    signal_for(g, FLAG_Z, seq0 + 2, sg, zp, g->off_z);
+    fill_ptrs(g, g->off_u, up);
+    long long row = 0;                                               // index into the carried rows (global order)
+    for (long long LB = 0; g->blk(LB, g->rank) < g->nblocks; LB++) {
+      const long long b = g->blk(LB, g->rank);
+      const long long g0 = b * db, g1 = g0 + g->block_rows(b);
+      if (g1 <= n) continue;
+      const long long first = std::max(g0, n);
+      if (g0 <= n && n < g1) {                                       // this block holds z^T
+        PeerCopy pc{};
+        pc.src = g->carried + row * ld; pc.lds = ld; pc.ldd = n; pc.rows = 1; pc.width = n; pc.P = P;
+        for (int r = 0; r < MAX_PEERS; r++) pc.dst[r] = zp[r] ? static_cast<double*>(zp[r]) : nullptr;
+        peer_copy_kernel<<<64, 256, 0, s>>>(pc);
+        instr().launches++;
+        MG_CU(cudaGetLastError());
+      }
+      const long long t0 = std::max(g0, n + 1) - (n + 1), t1 = g1 - (n + 1);   // identity rows of this block
+      if (t1 > t0) {
+        const double* src = g->carried + (row + (n + 1 + t0 - first)) * ld;
+        const long long cfirst = t0 & ~1ll;                          // U is upper triangular: columns >= t0 only
+        for (int r = 0; r < P; r++) {
+          if (up[r] == nullptr || (g->emulate && r != g->rank)) continue;
+          MG_CU(cudaMemcpy2DAsync(static_cast<double*>(up[r]) + t0 * ld + cfirst, (size_t)ld * 8, src + cfirst,
+                                  (size_t)ld * 8, (size_t)(n - cfirst) * 8, (size_t)(t1 - t0), cudaMemcpyDeviceToDevice, s));
+        }
+      }
+      row += g1 - first;
+    }
+    flag_kernel<<<1, 1, 0, s>>>(sg);
+    instr().launches++;
+    MG_CU(cudaGetLastError());
+    MG_RC(wait_all(g, s, FLAG_Z, seq0 + 2, info_dev));
+  }
+  MG_CU(launch_upper_gemv(s, Uloc, ld, zloc, n, g->alpha));          // a = U z, on every rank
+  // ---- 3. this rank's strip of A^-1 = U U^T and its contraction with dK/dtheta ----
+  const long long r0 = g->strip_r0, r1 = g->strip_r1;
+  if (r1 > r0) {
+    GemmParams u{};
+    u.A = Uloc + r0 * ld; u.lda = ld;
+    u.B = Uloc;           u.ldb = ld;
+    u.C = g->strip;       u.ldc = g->strip_ld;
+    u.M = (int)(r1 - r0); u.N = (int)r1; u.K = (int)n; u.lower = 1;
+    u.cyc_db = 1 << 30; u.cyc_p = 1; u.base_shift = (int)r0;       // local row r may touch columns <= r0 + r
+    u.k_from_row = 1; u.k_row0 = (int)r0;
+    MG_CU(launch_gemm_store_lower(s, u));
+  }
+  MG_CU(launch_grad_gram_strip(s, X, n, D, r0, r1 - r0, n_hidden, act, arch, hp_dev, g->tab3, n, g->strip, g->strip_ld,
+                               g->alpha, g->scal + SC_QUAD, kind, g->partial, g->slots));
+  MG_CU(launch_sum_slots(s, g->partial, g->slots, g->psum));
+  // ---- 4. partial sums of every rank -> every rank, fixed-order total, closed forms ----
+  {
+    void* gp[MAX_PEERS];
+    PeerSignal sg;
+    signal_for(g, FLAG_GRAD, seq0 + 3, sg, gp, g->off_gslots);
+    PeerCopy pc{};
+    pc.src = g->psum; pc.lds = 4; pc.ldd = 4; pc.rows = 1; pc.width = 4; pc.P = P;
+    for (int r = 0; r < MAX_PEERS; r++) pc.dst[r] = gp[r] ? static_cast<double*>(gp[r]) + 4 * g->rank : nullptr;
+    peer_copy_kernel<<<1, 32, 0, s>>>(pc);
+    flag_kernel<<<1, 1, 0, s>>>(sg);
+    instr().launches += 2;
+    MG_CU(cudaGetLastError());
+    MG_RC(wait_all(g, s, FLAG_GRAD, seq0 + 3, info_dev));
+    const double* slots = reinterpret_cast<const double*>(g->region + g->off_gslots);
+    if (g->emulate) MG_CU(launch_grad_finalize(s, slots + 4 * g->rank, 1, hp_dev, g->scal + SC_QUAD, kind, n, info_dev, grad_dev));
+    else MG_CU(launch_grad_finalize(s, slots, P, hp_dev, g->scal + SC_QUAD, kind, n, info_dev, grad_dev));
+  }
+  g->seq_base += (unsigned long long)npanels + 6;
   arm_watchdog(g, s, info_dev);
   return SMNNGP_OK;
 }

@@ -59,6 +59,7 @@ struct TmaShape {
   // the matrix or above the diagonal are skipped (producer and math warps decode alike).
   int super_rows;
   int cyc_alt;          // block-row-cyclic mask, snake distribution: extra shift of the rows of odd local blocks
+  int k_row0;           // k_from_row: global index of the output's first row (row strip of a larger matrix)
 };
 
 __host__ __device__ __forceinline__ long long tma_super_count_tiles(int M, int N, int lower, int sr) {
@@ -265,7 +266,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (!tma_decode(sh, t, ntn, cur, ti, tj)) continue;
         const int r0 = ti * TM_BM, c0 = tj * TM_BN;
         const int kt_end = tma_kt_end(sh, KT, c0);
-        for (int kt = sh.k_from_row ? r0 / BK : 0; kt < kt_end; kt++) {
+        for (int kt = sh.k_from_row ? (sh.k_row0 + r0) / BK : 0; kt < kt_end; kt++) {
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
           mbar_arrive_expect_tx(full0 + 8 * s, TM_STAGE_BYTES);
           const uint32_t dst = gring + s * TM_STAGE_BYTES;
@@ -300,7 +301,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
     const int kt_end = tma_kt_end(sh, KT, tj * TM_BN);
-    for (int kt = sh.k_from_row ? ti * (TM_BM / BK) : 0; kt < kt_end; kt++) {
+    for (int kt = sh.k_from_row ? (sh.k_row0 + ti * TM_BM) / BK : 0; kt < kt_end; kt++) {
       mbar_wait(full0 + 8 * s, ph);
       const uint32_t st = gring + s * TM_STAGE_BYTES;
       double a[2][MI], b[2][NI];

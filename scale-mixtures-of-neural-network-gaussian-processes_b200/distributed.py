@@ -367,7 +367,9 @@ class DistributedLML:
         h = C.c_void_p()
         with torch.cuda.device(dev):
             tc = getattr(self, "_tc", None)          # DistributedPredict: (test points, right-hand sides)
-            if tc is None:
+            if getattr(self, "_grad", False):        # DistributedGrad: identity rows ride along
+                ok = lib.smnngp_mg_create_grad(C.byref(h), self.rank, self.world, self.n, self.db) == 0
+            elif tc is None:
                 ok = lib.smnngp_mg_create(C.byref(h), self.rank, self.world, self.n, self.db) == 0
             else:
                 ok = lib.smnngp_mg_create_predict(C.byref(h), self.rank, self.world, self.n, tc[0], tc[1], self.db) == 0
@@ -700,6 +702,38 @@ class DistributedLML:
         if cuda:
             main.wait_stream(side)
         return sums, info, npanels
+
+
+class DistributedGrad(DistributedLML):
+    """SPR.loss and its gradient w.r.t. the six scalars (what objax.GradValues(model.loss, model.vars()) returns in the
+    reference's train step, experiments/regression/train.py:62-66, before the softplus chain rule) on the ranks of a
+    process group: one C call per rank (smnngp_lml_grad_mg_f64, csrc/multigpu.cu).  Needs the peer-store exchange
+    (CUDA, 2..8 ranks of one node, or emulate=(1, 0) for a one-rank job)."""
+
+    def __init__(self, n, d, spec: StackSpec, device, **kw):
+        self._grad = True
+        kw.setdefault("exchange", "peer")
+        super().__init__(n, d, spec, device, extra_rows=int(n) + 1, **kw)
+        if self.mg is None:
+            raise RuntimeError("DistributedGrad needs the C multi-GPU driver (peer-store exchange)")
+
+    @_on_own_device
+    def lml_grad(self, x, y, hp, kind="student_t"):
+        """(out[4] = {log p, loss, sum log L_ii, ||L^-1 y||^2}, grad[6] = d loss / d hp, info), identical on every rank"""
+        be = self.be
+        nh, act, arch = self.spec.ids()
+        x, y = x.contiguous(), y.contiguous()
+        out, grad = be.empty(4), be.empty(6)
+        info = be.zeros(1, dtype=torch.int32)
+        rc = be.lib.smnngp_lml_grad_mg_f64(self.mg, be._s(), be._p(x), be._p(y), x.shape[1], nh, act, arch, be._p(hp),
+                                           KIND[kind], be._p(out), be._p(grad), be._p(info))
+        if rc != 0:
+            raise RuntimeError("smnngp_lml_grad_mg_f64 failed: " + be.lib.smnngp_mg_last_error().decode())
+        return out, grad, info
+
+    def lml(self, x, y, hp, kind="student_t"):
+        out, _, info = self.lml_grad(x, y, hp, kind)
+        return out, info
 
 
 class DistributedPredict(DistributedLML):

@@ -191,6 +191,93 @@ def test_single_rank_predict_drivers_match_oracle(n, t, c, db, driver, monkeypat
     job.close()
 
 
+@pytest.mark.parametrize("n,db,act,kind", [(1500, 128, "relu", "student_t"), (2600, 256, "erf", "gauss"),
+                                           (3000, 512, "relu", "student_t")])
+def test_single_rank_distributed_gradient_matches_oracle(n, db, act, kind):
+    """smnngp_lml_grad_mg_f64 at world size 1 (identity rows carried through the block-cyclic factorisation with the
+    active-row limit, U copied through the peer region, strip SYRK from the diagonal, strip dual Gram pass, partial sums
+    through the peer slots): value and gradient against the oracle and against the single-GPU fused call"""
+    import torch
+    import smnngp_b200 as sm
+    from oracle import nngp_oracle as orc
+    from smnngp_b200.distributed import DistributedGrad
+    from tests.synth import regression_data, DEFAULT_HP as hp0
+    d = 8
+    hp = dict(hp0, b_std=0.3 if act == "erf" else hp0["b_std"], eps=1e-4)
+    x, y, *_ = regression_data(n, d)
+    spec = sm.StackSpec(3, act, "mlp")
+    job = DistributedGrad(n, d, spec, "cuda", block=db, emulate=(1, 0))
+    hpd = sm.make_hp(**hp)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    kw = dict(num_hiddens=3, act=act, arch="mlp", w_std=hp["w_std"], b_std=hp["b_std"], last_w_std=hp["last_w_std"],
+              eps=hp["eps"], kind=kind, a=hp["alpha"], b=hp["beta"])
+    lref, gref = orc.spr_loss_grad(x, y, **kw)
+    o1, g1, _ = sm.device.lml_grad(xd, yd, spec=spec, hp=hpd, kind=kind)
+    for _ in range(2):
+        out, grad, info = job.lml_grad(xd, yd, hpd, kind=kind)
+        g = grad.cpu().numpy()
+        assert int(info.item()) == 0
+        assert abs(out[1].item() - lref) <= 1e-8 * abs(lref)
+        assert np.all(np.abs(g - gref) <= 1e-6 * np.abs(gref) + 1e-10 * np.abs(gref).max()), (g, gref)
+        assert np.all(np.abs(g - g1.cpu().numpy()) <= 1e-9 * np.abs(gref) + 1e-12 * np.abs(gref).max())
+    job.close()
+
+
+def _grad_worker(rank, world, port, n, d, db, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import smnngp_b200 as sm
+        from smnngp_b200.distributed import DistributedGrad
+        from tests.synth import regression_data, DEFAULT_HP as hp0
+        hp = dict(hp0, eps=1e-4)
+        x, y, *_ = regression_data(n, d)
+        dev = torch.device("cuda", rank)
+        job = DistributedGrad(n, d, sm.StackSpec(3, "relu", "mlp"), dev, block=db)
+        xd, yd, hpd = torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), sm.make_hp(device=dev, **hp)
+        out, grad, info = job.lml_grad(xd, yd, hpd)
+        out2, grad2, _ = job.lml_grad(xd, yd, hpd)
+        assert grad2.cpu().tolist() == grad.cpu().tolist() and out2.cpu().tolist() == out.cpu().tolist()
+        q.put((rank, out.cpu().tolist(), grad.cpu().tolist(), int(info.item())))
+        job.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,db", [(2900, 128), (3000, 256), (1501, 128)])
+def test_two_rank_gradient_matches_oracle(n, db):
+    import torch
+    import torch.multiprocessing as mp
+    from oracle import nngp_oracle as orc
+    from tests.synth import regression_data, DEFAULT_HP as hp0
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + n % 100
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, n, 8, db, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    hp = dict(hp0, eps=1e-4)
+    x, y, *_ = regression_data(n, 8)
+    lref, gref = orc.spr_loss_grad(x, y, num_hiddens=3, act="relu", arch="mlp", w_std=hp["w_std"], b_std=hp["b_std"],
+                                   last_w_std=hp["last_w_std"], eps=hp["eps"], kind="student_t", a=hp["alpha"], b=hp["beta"])
+    for rank, out, grad, info in res:
+        g = np.array(grad)
+        assert info == 0 and abs(out[1] - lref) <= 1e-8 * abs(lref)
+        assert np.all(np.abs(g - gref) <= 1e-6 * np.abs(gref) + 1e-10 * np.abs(gref).max()), (g, gref)
+    assert res[0][2] == res[1][2]
+
+
 def _predict_worker(rank, world, port, n, t, c, d, db, q, exchange):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
