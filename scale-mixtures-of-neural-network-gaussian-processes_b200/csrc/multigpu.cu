@@ -126,14 +126,25 @@ struct smnngp_mg {
     const int j = (int)(x % P);
     return ((x / P) & 1) ? P - 1 - j : j;
   }
-  // model of the update work of block row b: rows x (global position)^2 (it is updated by b panels, each over ~b/2
-  // column blocks); returns the largest per-rank load of an assignment
+  // model of the update work of a block of rows, in the same units for both kinds of rows:
+  //   square rows (and y^T / right-hand-side / test rows) at global position pos: updated by pos / db panels, each over
+  //   (pos - c1) columns -> rows x pos^2 (capped at n^2 for carried rows, which span all n columns);
+  //   identity rows of the gradient handle, identity index i: inactive until the panel that holds column i, then
+  //   updated over the remaining (n - c1) columns of every later panel -> rows x (n - i)^2.
+  // Returns the largest per-rank load of an assignment.
   double max_load(int shift) const {
     std::vector<double> w((size_t)P, 0.0);
     for (long long b = 0; b < nblocks; b++) {
       const int r = shift < 0 ? (int)(b % P) : snake_owner(b, shift);
       const double pos = ((double)b + 0.5) * (double)db;
-      w[r] += (double)block_rows(b) * pos * pos;
+      double wgt;
+      if (grad && pos > (double)(n + c)) {
+        const double rest = std::max(0.0, (double)n - (pos - (double)(n + c)));
+        wgt = rest * rest;
+      } else {
+        wgt = std::min(pos, (double)n) * std::min(pos, (double)n);
+      }
+      w[r] += (double)block_rows(b) * wgt;
     }
     return *std::max_element(w.begin(), w.end());
   }
