@@ -4,6 +4,10 @@ same model construction, same Adam-on-softplus-variables loop, same NaN stop - e
 
     python examples/regression_train.py --method tp --num-hiddens 3 --max-steps 200
 
+On several GPUs (one process per GPU; every step is one smnngp_lml_grad_mg_f64 call per rank):
+
+    torchrun --standalone --nproc-per-node 2 examples/regression_train.py --distributed --rows 20000 --max-steps 50
+
 Synthetic UCI-shaped data (no dataset download in this environment); swap `make_data` for the reference's
 `get_dataset` / `split_dataset` (experiments/regression/data.py) to reproduce its runs."""
 import argparse
@@ -32,6 +36,9 @@ def build_model(args, x_train, y_train, y_mean, y_std):
 
     kernel = NNGPKernel(get_kernel_fn, args.w_std, args.b_std, args.last_w_std)            # train.py:126
     lik = StudentTLikelihood(args.alpha, args.beta) if args.method == "tp" else GaussianLikelihood()
+    if getattr(args, "distributed", False):
+        from smnngp_b200.spax import DistributedSPR
+        return DistributedSPR(kernel, lik, x_train, y_train, y_mean, y_std, eps=args.epsilon)
     return SPR(kernel, lik, x_train, y_train, y_mean, y_std, eps=args.epsilon)             # train.py:137-142
 
 
@@ -77,15 +84,32 @@ def parse(argv=None):
     p.add_argument("-s", "--seed", type=int, default=10)
     p.add_argument("--rows", type=int, default=4000)
     p.add_argument("--features", type=int, default=8)
+    p.add_argument("--distributed", action="store_true", help="under torchrun: shard every step over the ranks' GPUs")
     return p.parse_args(argv)
 
 
 def main(argv=None):
     args = parse(argv)
     (x, y), valid, test, (y_std, y_mean) = make_data(args.rows, args.rows // 8, args.rows // 8, args.features, args.seed)
+    log = print
+    if args.distributed:
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=dev)
+        to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        x, y, valid, test = to_dev(x), to_dev(y), tuple(map(to_dev, valid)), tuple(map(to_dev, test))
+        if dist.get_rank() != 0:
+            log = lambda *a, **k: None
     model = build_model(args, x, y, y_mean, y_std)
-    best = train(model, args, valid, test)
-    print(f"[{best[0]:5d}] NLL: {best[1]:.5f}  TEST: {best[2]:.5f}")
+    best = train(model, args, valid, test, log=log)
+    log(f"[{best[0]:5d}] NLL: {best[1]:.5f}  TEST: {best[2]:.5f}")
+    if args.distributed:
+        model.close()
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

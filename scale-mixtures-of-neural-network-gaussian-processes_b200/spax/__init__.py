@@ -1,6 +1,6 @@
 from .kernels import NNGPKernel
 from .likelihoods import Likelihood, GaussianLikelihood, StudentTLikelihood
-from .models import SPR
+from .models import SPR, DistributedSPR
 from .utils import jitter, multivariate_t_logpdf, multivariate_normal_logpdf
 from .base import Module, TrainVar, ConstraintTrainVar
 from .bijectors import positive

@@ -11,7 +11,7 @@ from .utils import jitter
 from .. import device as _dev
 from ..nt_kernels import KernelFn
 
-__all__ = ["SPR"]
+__all__ = ["SPR", "DistributedSPR"]
 
 
 class SPR(Module):
@@ -89,3 +89,67 @@ class SPR(Module):
         log_prob = self.likelihood.logpdf((y * self.y_std) + self.y_mean, (mean.flatten() * self.y_std) + self.y_mean,
                                           cov * self.y_std ** 2, aux)
         return -torch.mean(log_prob)
+
+
+
+class DistributedSPR(SPR):
+    """SPR whose device work is sharded over the ranks of a torch.distributed process group (one process per GPU,
+    launched with torchrun): the same methods, every rank passes the same data and obtains the same numbers.
+
+        loss / loss_and_grad -> smnngp_lml_grad_mg_f64  (distributed.DistributedGrad)
+        test_nll             -> smnngp_test_nll_mg_f64  (distributed.DistributedPredict)
+
+    x_data / y_data must be torch CUDA tensors on this rank's device.  The solvers are created on first use (they own
+    the rank's row shard and the NVLink-visible buffers) and re-used by every later step - the reference evaluates the
+    same shapes for 30 000 steps (experiments/regression/train.py:178).  ``solvers=`` injects ready-made ones (tests)."""
+
+    def __init__(self, kernel, likelihood, x_data, y_data, y_mean, y_std, *, eps: float = 1e-6, group=None, block=None,
+                 solvers=None):
+        super().__init__(kernel, likelihood, x_data, y_data, y_mean, y_std, eps=eps)
+        self.group, self.block = group, block
+        self._grad_solver = (solvers or {}).get("grad")
+        self._predict_solvers = dict((solvers or {}).get("predict", {}))
+
+    def _spec_hp(self):
+        kernel_fn = self.kernel.get_kernel_fn()
+        if not self._fused(kernel_fn):
+            raise TypeError("DistributedSPR needs a kernel_fn built by smnngp nt_kernels and a spax likelihood")
+        return kernel_fn.spec, kernel_fn.hp(self.x_data.device, **self._hp_args())
+
+    def loss_and_grad(self):
+        from ..distributed import DistributedGrad
+        spec, hp = self._spec_hp()
+        if self._grad_solver is None:
+            self._grad_solver = DistributedGrad(self.num_data, self.x_data.shape[1], spec, self.x_data.device,
+                                                group=self.group, block=self.block)
+        out, grad, _ = self._grad_solver.lml_grad(self.x_data, self.y_data, hp, kind=self.likelihood.kind)
+        g = grad.cpu().numpy()
+        slots = {"kernel.w_std": (self.kernel.w_std, 0), "kernel.b_std": (self.kernel.b_std, 1),
+                 "kernel.last_w_std": (self.kernel.last_w_std, 2), "eps": (self.eps, 3)}
+        if hasattr(self.likelihood, "a"):
+            slots["likelihood.a"] = (self.likelihood.a, 4)
+            slots["likelihood.b"] = (self.likelihood.b, 5)
+        grads = {name: float(g[i]) * float(var.constraint.grad(var.value)) for name, (var, i) in slots.items()}
+        return float(out[1]), grads
+
+    def loss(self):
+        return self.loss_and_grad()[0]
+
+    def test_nll(self, x, y):
+        from ..distributed import DistributedPredict
+        spec, hp = self._spec_hp()
+        t = int(x.shape[0])
+        solver = self._predict_solvers.get(t)
+        if solver is None:
+            solver = DistributedPredict(self.num_data, self.x_data.shape[1], t, 1, spec, self.x_data.device,
+                                        group=self.group, block=self.block)
+            self._predict_solvers[t] = solver
+        nll, _, _, _ = solver.test_nll(self.x_data, self.y_data, x, y, float(self.y_mean), float(self.y_std), hp,
+                                       kind=self.likelihood.kind)
+        return nll[0]
+
+    def close(self):
+        for s in [self._grad_solver, *self._predict_solvers.values()]:
+            if s is not None and hasattr(s, "close"):
+                s.close()
+        self._grad_solver, self._predict_solvers = None, {}

@@ -99,3 +99,46 @@ def test_adam_matches_objax_update_rule():
     g = float(positive().grad(v.value))
     h = 1e-6
     assert abs(g - (float(positive()(v.value + h)) - float(positive()(v.value - h))) / (2 * h)) <= 1e-8
+
+
+def test_distributed_spr_glue_with_injected_solvers():
+    """DistributedSPR host logic without GPUs: the solvers are injected (oracle-backed stand-ins with the interface of
+    distributed.DistributedGrad / DistributedPredict); the softplus chain rule and the variable naming must match SPR's"""
+    import torch
+    import smnngp_b200 as sm
+    from oracle import nngp_oracle as orc
+    from smnngp_b200.spax import NNGPKernel, StudentTLikelihood, DistributedSPR
+    from tests.synth import regression_data, DEFAULT_HP as hp
+    x, y, xt, yt, ym, ys = regression_data(300, 5, t=40)
+    kw = dict(num_hiddens=2, act="relu", arch="mlp")
+
+    class GradStub:
+        def lml_grad(self, xd, yd, hpd, kind="student_t"):
+            h = hpd.tolist()
+            loss, g = orc.spr_loss_grad(xd.numpy(), yd.numpy(), w_std=h[0], b_std=h[1], last_w_std=h[2], eps=h[3], kind=kind,
+                                        a=h[4], b=h[5], **kw)
+            return torch.tensor([0.0, loss, 0.0, 0.0], dtype=torch.float64), torch.from_numpy(np.asarray(g)), torch.zeros(1)
+
+    class PredictStub:
+        def test_nll(self, xd, yd, xtd, ytd, y_mean, y_std, hpd, kind="student_t"):
+            h = hpd.tolist()
+            nll = orc.spr_test_nll(xd.numpy(), yd.numpy(), xtd.numpy(), ytd.numpy(), y_mean, y_std, w_std=h[0], b_std=h[1],
+                                   last_w_std=h[2], eps=h[3], kind=kind, a=h[4], b=h[5], **kw)
+            return torch.tensor([nll], dtype=torch.float64), None, None, torch.zeros(1)
+
+    def get_kernel_fn(w_std, b_std, last_w_std):
+        return sm.get_mlp_kernel(2, act="relu", w_std=w_std, b_std=b_std, last_w_std=last_w_std)
+
+    model = DistributedSPR(NNGPKernel(get_kernel_fn, 1.2, 0.3, 0.8), StudentTLikelihood(2.5, 1.5), torch.from_numpy(x),
+                           torch.from_numpy(y), ym, ys, eps=1e-3, solvers={"grad": GradStub(), "predict": {40: PredictStub()}})
+    loss, grads = model.loss_and_grad()
+    assert set(grads) == set(model.vars())
+    lref, gref = orc.spr_loss_grad(x, y, w_std=1.2, b_std=0.3, last_w_std=0.8, eps=1e-3, kind="student_t", a=2.5, b=1.5, **kw)
+    assert abs(loss - lref) <= 1e-12 * abs(lref)
+    # chain rule through softplus: d loss / d raw = d loss / d safe * sigmoid(raw)
+    raw = float(model.kernel.w_std.value)
+    assert abs(grads["kernel.w_std"] - gref[0] / (1.0 + np.exp(-raw))) <= 1e-10 * abs(gref[0])
+    nll = float(model.test_nll(torch.from_numpy(xt), torch.from_numpy(yt)))
+    ref = orc.spr_test_nll(x, y, xt, yt, ym, ys, w_std=1.2, b_std=0.3, last_w_std=0.8, eps=1e-3, kind="student_t", a=2.5,
+                           b=1.5, **kw)
+    assert abs(nll - ref) <= 1e-12 * abs(ref)
