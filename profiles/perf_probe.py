@@ -21,6 +21,8 @@ which = sys.argv[1:] or ["potrf", "gram", "lml"]
 sm._lib.load().smnngp_set_tile_variant(int(os.environ.get("TILE", "0")))
 sm._lib.load().smnngp_set_lookahead(int(os.environ.get("LOOKAHEAD", "1")))
 nbs = [int(v) for v in os.environ.get("NBS", "0").split(",")]
+if "TAIL" in os.environ:
+    sm._lib.load().smnngp_set_tail_cols(int(os.environ["TAIL"]))
 if "RESERVE" in os.environ:
     a_, b_ = (int(v) for v in os.environ["RESERVE"].split(","))
     sm._lib.load().smnngp_set_lookahead_reserve(a_, b_)

@@ -26,7 +26,7 @@ EXPORTS = [
     "smnngp_lml_workspace_bytes", "smnngp_lml_f64", "smnngp_lml_grad_workspace_bytes", "smnngp_lml_grad_f64",
     "smnngp_lml_grad_host_f64", "smnngp_predict_workspace_bytes", "smnngp_predict_f64", "smnngp_predict_cov_f64",
     "smnngp_test_nll_f64", "smnngp_lml_host_f64", "smnngp_predict_host_f64", "smnngp_test_nll_host_f64",
-    "smnngp_host_release", "smnngp_set_panel_width", "smnngp_set_tile_variant", "smnngp_debug_occupancy", "smnngp_set_lookahead", "smnngp_set_fused_panel", "smnngp_set_gram_super_rows", "smnngp_set_lookahead_reserve", "smnngp_debug_potf2_clocks",
+    "smnngp_host_release", "smnngp_set_panel_width", "smnngp_set_tile_variant", "smnngp_debug_occupancy", "smnngp_set_lookahead", "smnngp_set_fused_panel", "smnngp_set_tail_cols", "smnngp_set_gram_super_rows", "smnngp_set_lookahead_reserve", "smnngp_debug_potf2_clocks",
     "smnngp_sample_f_iid_f64", "smnngp_draw_metrics_f64",
     "smnngp_grid_base_f64", "smnngp_grid_workspace_bytes", "smnngp_grid_point_f64",
     "smnngp_stage_qtable_f64", "smnngp_stage_gram_f64", "smnngp_stage_factor_diag_f64", "smnngp_stage_trsm_f64",
@@ -183,6 +183,8 @@ def _declare(lib):
     lib.smnngp_set_lookahead.argtypes = [_i]
     lib.smnngp_set_fused_panel.restype = None
     lib.smnngp_set_fused_panel.argtypes = [_i]
+    lib.smnngp_set_tail_cols.restype = None
+    lib.smnngp_set_tail_cols.argtypes = [_i64]
     lib.smnngp_set_gram_super_rows.restype = None
     lib.smnngp_set_gram_super_rows.argtypes = [_i, _i64]
     lib.smnngp_grid_base_f64.argtypes = [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _vp]

@@ -148,6 +148,8 @@ int smnngp_debug_occupancy(int variant) { return debug_gemm_occupancy(variant); 
 void smnngp_set_lookahead(int on) { lookahead_mode() = on ? 1 : 0; }
 // 1 (default): single-launch panel solve with the diagonal block's full inverse; 0: 128-block substitution in place
 void smnngp_set_fused_panel(int on) { dctx().fused_panel = on ? 1 : 0; }
+// the look-ahead factorisation (N >= 8192) hands its last <= cols columns to the single-stream 128-column path; 0: never
+void smnngp_set_tail_cols(int64_t cols) { dctx().tail_cols = cols < 0 ? 0 : cols; }
 // super-tile height (128-row tiles) of the Gram kernel's L2-aware tile walk; 0 = row-major walk (round-1 behaviour)
 void smnngp_set_gram_super_rows(int sr, int64_t min_operand_bytes) {
   dctx().gram_super = sr < 0 ? 0 : (sr > 64 ? 64 : sr);

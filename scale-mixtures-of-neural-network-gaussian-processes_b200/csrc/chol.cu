@@ -635,7 +635,17 @@ cudaError_t potrf_trapezoid(cudaStream_t s, double* A, long long lda, long long 
   const long long ldp = FUSED_LD;
   LA_CK(cudaEventRecord(la->ev_fork, s));
   LA_CK(cudaStreamWaitEvent(la->side, la->ev_fork, 0));
+  const long long tail = NB >= 4 * PB ? la->tail_cols : 0;
   for (long long c0 = 0; c0 < N; c0 += NB) {
+    if (c0 > 0 && N - c0 <= tail) {
+      // Tail: once the trailing matrix is this small every 512-wide panel costs ~0.5 ms of chain (diagonal block,
+      // inverse, one-wave panel solve) against < 0.1 ms of update.  The plain single-stream 128-column factorisation
+      // (diagonal kernel + one TRSM + one update per step, ~75-95 us per 128 columns) is faster from here on.
+      LA_CK(cudaEventRecord(la->ev_diag, la->side));          // the side stream's last update_a
+      LA_CK(cudaStreamWaitEvent(s, la->ev_diag, 0));
+      return potrf_serial(s, A + c0 * lda + c0, lda, Mfull - c0, N - c0, PB, Linv_base, logdet, info, 0, (int)c0, false,
+                          ident_row0);
+    }
     const long long c1 = (c0 + NB < N) ? c0 + NB : N;
     const int w = (int)(c1 - c0);
     const long long Mtot = active_rows(Mfull, ident_row0, c1);
