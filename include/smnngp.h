@@ -342,7 +342,7 @@ void smnngp_set_lookahead(int on);
 void smnngp_set_fused_panel(int on);
 /* tuning knob: the look-ahead factorisation (N >= 8192, 512-wide panels) hands its last <= cols columns to the
  * single-stream 128-column path, whose per-step chain is shorter than a 512-wide panel's once the trailing update is
- * small.  Default 4096; 0 = never.  Applies to the current device. */
+ * small.  Default 2048 (measured: 10.07 -> 9.81 ms at N = 8192; 4096 is slower); 0 = never.  Applies to the current device. */
 void smnngp_set_tail_cols(int64_t cols);
 /* tuning knob: L2-aware tile walk of the Gram kernel - tiles are visited in square super-tiles of `sr` x 2 sr tiles
  * (128 sr elements a side) so that the operand rows of the tiles in flight stay L2 resident; 0 = row-major walk.
