@@ -33,6 +33,7 @@ struct DeviceCtx {
   int tile_variant = 0, lookahead = 1, la_reserve[2] = {8, 0}, panel_width = 0, fused_panel = 1, gram_super = 8;
   long long tail_cols = 2048;   // look-ahead factorisation (512-wide panels) hands the last <= tail_cols columns to the serial path
   long long gram_super_min_bytes = 40000000;   // B operand (M x D doubles) below this: plain row-major walk
+  int peer_wait_mode = 0;       // smnngp_set_peer_wait_mode (exchange.cu)
   long long* potf2_clk = nullptr;
   // look-ahead side stream of the fused factorisation
   cudaStream_t side = nullptr;

@@ -158,10 +158,9 @@ PFN_streamWaitValue64 stream_wait_fn() {
   }();
   return fn;
 }
-int& wait_mode() {
-  static int m = 0;      // 0 = stream memory operation (default), 1 = one-thread spin kernel with timeout
-  return m;
-}
+// 0 = stream memory operation (default: no SM is held; the time-out is the caller's watchdog - csrc/multigpu.cu has one
+// per handle, distributed.py one per driver), 1 = one-thread spin kernel with its own time-out.  Per-device knob.
+int& wait_mode() { return dctx().peer_wait_mode; }
 
 void fill_signal(PeerSignal& sg, void* const* flag_ptrs, int P, long long flag_index, unsigned long long seq,
                  unsigned int* counter) {

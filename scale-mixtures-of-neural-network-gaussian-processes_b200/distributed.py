@@ -174,6 +174,45 @@ def _on_own_device(method):
     return wrapped
 
 
+class StreamWatchdog:
+    """Dead-peer protection of the Python panel loop (the C driver has its own, csrc/multigpu.cu): the flag waits are
+    stream memory operations without a time-out, so after every evaluation an event is recorded and a daemon thread
+    polls it; if it has not completed after ``timeout_s`` the thread writes every flag word of this rank (the waits
+    compare cyclically: a value far ahead of any sequence number satisfies them all) and poisons ``info`` - the stream
+    drains and the results are NaN instead of the GPU hanging for ever."""
+
+    def __init__(self, flags, timeout_s):
+        self.flags, self.timeout_s = flags, float(timeout_s)          # flags: int64 tensor view of the local flag words
+        self.fired = False
+
+    def _release(self, info, seq_hint):
+        self.fired = True
+        side = torch.cuda.Stream(device=self.flags.device) if self.flags.is_cuda else None
+        ctx = torch.cuda.stream(side) if side is not None else _NullCtx()
+        with ctx:
+            if info is not None:
+                info.fill_(0x7fffffff)
+            self.flags.fill_(int(seq_hint) + (1 << 40))
+        if side is not None:
+            side.synchronize()
+
+    def watch(self, event, info, seq_hint, poll_s=0.05):
+        import threading
+        import time
+
+        def run():
+            t0 = time.monotonic()
+            while not event.query():
+                if time.monotonic() - t0 > self.timeout_s:
+                    self._release(info, seq_hint)
+                    return
+                time.sleep(poll_s)
+
+        th = threading.Thread(target=run, daemon=True)
+        th.start()
+        return th
+
+
 class PeerUnavailable(RuntimeError):
     """raised on EVERY rank when the peer-memory exchange cannot be set up on some rank"""
 
@@ -319,6 +358,7 @@ class DistributedLML:
         self.exchange = exchange
         self.px = None
         self.mg = None
+        self._dog = None
         # exchange == "peer": the whole evaluation is ONE C call per rank (csrc/multigpu.cu, smnngp_lml_mg_f64); the
         # Python panel loop below remains for the NCCL exchange, the NumPy backend of the CPU suite, the predictive
         # driver (DistributedPredict) and as a cross-check (SMNNGP_MG_DRIVER=python)
@@ -631,6 +671,13 @@ class DistributedLML:
                 be.sumsq(self.a[lrow, :n], sums[1:2])
         if self.px is not None:
             self.seq_base += npanels + 1
+            if self.a.is_cuda and not self.emulate:                     # dead-peer watchdog of the Python panel loop
+                ev = torch.cuda.Event()
+                ev.record()
+                if self._dog is None:
+                    flags = torch.as_tensor(_RawCuda(self.px.local + self.px.off_flags, (32,), "<i8"), device=self.a.device)
+                    self._dog = StreamWatchdog(flags, self.wait_timeout_s)
+                self._dog.watch(ev, info, self.seq_base)
         if P > 1 and not self.emulate:
             dist.all_reduce(sums, group=self.group)
             dist.all_reduce(info, op=dist.ReduceOp.MAX, group=self.group)

@@ -244,3 +244,24 @@ def test_c_driver_block_layouts(world, n, block):
     assert res[3] <= res[0] + 1e-12 and res[3] <= res[1] + 1e-12 and res[3] <= res[2] + 1e-12
     if world == 8 and n == 60000:
         assert res[0] > 1.08 and res[3] < 1.03          # 8.6 % -> 2.5 % over the mean (profiles/r02_layouts_8gpu.txt)
+
+
+def test_stream_watchdog_releases_waits_and_poisons_info():
+    """dead-peer protection of the Python panel loop: an event that never completes makes the watchdog write every flag
+    word far ahead of any sequence number and set info = INT_MAX; a completed event leaves everything alone"""
+    from smnngp_b200.distributed import StreamWatchdog
+
+    class Ev:
+        def __init__(self, done):
+            self.done = done
+
+        def query(self):
+            return self.done
+
+    flags = torch.zeros(32, dtype=torch.int64)
+    info = torch.zeros(1, dtype=torch.int32)
+    dog = StreamWatchdog(flags, timeout_s=0.2)
+    dog.watch(Ev(True), info, 1234).join(timeout=5)
+    assert not dog.fired and int(info.item()) == 0 and int(flags.abs().sum()) == 0
+    dog.watch(Ev(False), info, 1234, poll_s=0.02).join(timeout=5)
+    assert dog.fired and int(info.item()) == 0x7fffffff and bool((flags >= 1234 + (1 << 40)).all())
