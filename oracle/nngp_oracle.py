@@ -178,16 +178,61 @@ def jitter(num, eps=1e-6):
 # ----------------------------------------------------------------------------------------------------------
 # marginal likelihoods: spax/utils.py:160-183, spax/likelihoods.py:25-28, :45-50, spax/models.py:93-98
 # ----------------------------------------------------------------------------------------------------------
+# SciPy's LAPACK interface uses 32-bit integers: one potrf / trtrs call on a matrix with more than 2^31 elements
+# (N >= 46 341) segfaults.  Above this order the factorisation and the forward substitution run block by block
+# (right-looking, LAPACK potrf on the diagonal block, trsm for the panel, gemm for the trailing blocks): the same LAPACK /
+# BLAS family, the same arithmetic up to the usual blocked-algorithm rounding (checked in tests/test_oracle_cpu.py).
+BLOCKED_ABOVE = 40000
+
+
+def cholesky_blocked_inplace(a, nb=8192):
+    """Lower Cholesky factor of the symmetric a (C-order, lower part read) IN PLACE, nb-wide panels."""
+    n = a.shape[0]
+    for k0 in range(0, n, nb):
+        k1 = min(k0 + nb, n)
+        lkk = sla.cholesky(a[k0:k1, k0:k1], lower=True, check_finite=False)
+        a[k0:k1, k0:k1] = lkk
+        if k1 == n:
+            break
+        panel = a[k1:, k0:k1]
+        panel[...] = sla.solve_triangular(lkk, panel.T, lower=True, check_finite=False).T      # panel L_kk^-T
+        for i0 in range(k1, n, nb):
+            i1 = min(i0 + nb, n)
+            a[i0:i1, k1:i1] -= panel[i0 - k1:i1 - k1] @ panel[:i1 - k1].T
+    return a
+
+
+def forward_substitution_blocked(L, y, nb=8192):
+    """z = L^-1 y with the lower factor stored in the lower part of L (blocks of nb rows)."""
+    n = L.shape[0]
+    z = np.array(y, dtype=np.float64)
+    for k0 in range(0, n, nb):
+        k1 = min(k0 + nb, n)
+        if k0 > 0:
+            z[k0:k1] -= L[k0:k1, :k0] @ z[:k0]
+        z[k0:k1] = sla.solve_triangular(L[k0:k1, k0:k1], z[k0:k1], lower=True, check_finite=False)
+    return z
+
+
+def _chol_and_solve(shape, rhs):
+    """(L, L^-1 rhs) for the SPD matrix `shape`; raises scipy.linalg.LinAlgError when it is not positive definite.
+    Large matrices are factored block-wise IN PLACE (`shape` is overwritten: callers pass a temporary)."""
+    if shape.shape[0] > BLOCKED_ABOVE:
+        L = cholesky_blocked_inplace(shape)
+        return L, forward_substitution_blocked(L, rhs)
+    L = sla.cholesky(shape, lower=True, check_finite=False)
+    return L, sla.solve_triangular(L, rhs, lower=True, check_finite=False)
+
+
 def multivariate_t_logpdf(x, loc, shape, df):
     """spax/utils.py:178-183: Cholesky, L^-1 (x - loc), closed form."""
     x = np.asarray(x, dtype=np.float64)
     n = x.shape[-1]
     t = 0.5 * (df + n)
     try:
-        L = sla.cholesky(shape, lower=True, check_finite=False)
+        L, y = _chol_and_solve(shape, x - loc)
     except sla.LinAlgError:
         return float("nan")                                         # jax cholesky: NaN on non-PD, no raise
-    y = sla.solve_triangular(L, x - loc, lower=True, check_finite=False)
     return float(-t * np.log(1.0 + (1.0 / df) * (y @ y)) - n / 2 * np.log(df * np.pi) + gammaln(t)
                  - gammaln(0.5 * df) - np.log(np.diag(L)).sum())
 
@@ -197,10 +242,9 @@ def multivariate_normal_logpdf(x, mean, cov):
     x = np.asarray(x, dtype=np.float64)
     n = x.shape[-1]
     try:
-        L = sla.cholesky(cov, lower=True, check_finite=False)
+        L, y = _chol_and_solve(cov, x - mean)
     except sla.LinAlgError:
         return float("nan")
-    y = sla.solve_triangular(L, x - mean, lower=True, check_finite=False)
     return float(-0.5 * (y @ y) - n / 2 * np.log(2 * np.pi) - np.log(np.diag(L)).sum())
 
 
@@ -208,6 +252,9 @@ def prior_logpdf(y, cov, *, kind, a=None, b=None):
     """Likelihood.prior_logpdf: kind 'student_t' (likelihoods.py:45-50) or 'gauss' (:25-28)."""
     zero = np.zeros_like(y)
     if kind == "student_t":
+        if cov.shape[0] > BLOCKED_ABOVE:      # scale in place: a second N x N array would not fit next to the first
+            cov *= b / a
+            return multivariate_t_logpdf(y, zero, cov, 2 * a)
         return multivariate_t_logpdf(y, zero, (b / a) * cov, 2 * a)
     if kind == "gauss":
         return multivariate_normal_logpdf(y, zero, cov)

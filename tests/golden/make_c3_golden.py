@@ -24,36 +24,6 @@ import scipy.linalg as sla
 from scipy.special import gammaln
 
 
-def cholesky_blocked_inplace(a, nb=8192):
-    """Lower Cholesky factor of the symmetric a (C-order, lower part read) in place, right-looking by nb-wide panels:
-    LAPACK potrf on the diagonal block, trsm for the panel, gemm for the trailing lower blocks."""
-    n = a.shape[0]
-    for k0 in range(0, n, nb):
-        k1 = min(k0 + nb, n)
-        lkk = sla.cholesky(a[k0:k1, k0:k1], lower=True, check_finite=False)
-        a[k0:k1, k0:k1] = lkk
-        if k1 == n:
-            break
-        panel = a[k1:, k0:k1]
-        panel[...] = sla.solve_triangular(lkk, panel.T, lower=True, check_finite=False).T      # panel L_kk^-T
-        for i0 in range(k1, n, nb):
-            i1 = min(i0 + nb, n)
-            a[i0:i1, k1:i1] -= panel[i0 - k1:i1 - k1] @ panel[:i1 - k1].T
-    return a
-
-
-def forward_substitution_blocked(L, y, nb=8192):
-    """z = L^-1 y with the lower factor stored in the lower part of L (blocks of nb rows)"""
-    n = L.shape[0]
-    z = np.array(y, dtype=np.float64)
-    for k0 in range(0, n, nb):
-        k1 = min(k0 + nb, n)
-        if k0 > 0:
-            z[k0:k1] -= L[k0:k1, :k0] @ z[:k0]
-        z[k0:k1] = sla.solve_triangular(L[k0:k1, k0:k1], z[k0:k1], lower=True, check_finite=False)
-    return z
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=60000)
@@ -82,9 +52,9 @@ def main():
         ref = (float(zr @ zr), float(np.log(np.diag(Lr)).sum()))
         del Lr
     t1 = time.perf_counter()
-    L = cholesky_blocked_inplace(cov, args.block)                          # spax/utils.py:179
+    L = orc.cholesky_blocked_inplace(cov, args.block)                      # spax/utils.py:179
     t_chol = time.perf_counter() - t1
-    z = forward_substitution_blocked(L, y, args.block)                     # spax/utils.py:180
+    z = orc.forward_substitution_blocked(L, y, args.block)                 # spax/utils.py:180
     logp = float(-t * np.log(1.0 + (1.0 / df) * (z @ z)) - n / 2 * np.log(df * np.pi) + gammaln(t)
                  - gammaln(0.5 * df) - np.log(np.diag(L)).sum())          # spax/utils.py:181-183
     loss = -logp / n                                                       # spax/models.py:98

@@ -205,6 +205,25 @@ def test_unsupported_act_and_arch():
         orc.nngp_gram(x, num_hiddens=1, arch="cnn")
 
 
+def test_blocked_cholesky_path_matches_one_call_lapack(monkeypatch):
+    """above N = 40 000 the oracle factors block by block (SciPy's 32-bit LAPACK interface segfaults past 2^31 elements);
+    forced on at a small size it must reproduce the one-call path: same loss, same factor"""
+    import scipy.linalg as sla
+    from tests.synth import regression_data
+    x, y, *_ = regression_data(700, 6)
+    kw = dict(num_hiddens=2, act="relu", arch="mlp", w_std=1.1, b_std=0.2, last_w_std=0.9, eps=1e-4, a=2.0, b=3.0)
+    ref_t = orc.spr_loss(x, y, kind="student_t", **kw)
+    ref_g = orc.spr_loss(x, y, kind="gauss", **kw)
+    monkeypatch.setattr(orc, "BLOCKED_ABOVE", 100)
+    assert abs(orc.spr_loss(x, y, kind="student_t", **kw) - ref_t) <= 1e-13 * abs(ref_t)
+    assert abs(orc.spr_loss(x, y, kind="gauss", **kw) - ref_g) <= 1e-13 * abs(ref_g)
+    k = orc.nngp_gram(x, num_hiddens=2, act="relu", w_std=1.1, b_std=0.2, last_w_std=0.9) + 1e-4 * np.eye(700)
+    L = orc.cholesky_blocked_inplace(k.copy(), nb=128)
+    assert np.abs(np.tril(L) - sla.cholesky(k, lower=True)).max() <= 1e-12
+    z = orc.forward_substitution_blocked(L, y, nb=128)
+    assert np.abs(z - sla.solve_triangular(np.tril(L), y, lower=True)).max() <= 1e-10 * np.abs(z).max()
+
+
 # ---- host-side pieces of the product that need no GPU ---------------------------------------------------
 def test_cabi_library_loads_and_exports_every_declared_symbol():
     import smnngp_b200 as sm
