@@ -132,20 +132,20 @@ struct smnngp_mg {
   //   identity rows of the gradient handle, identity index i: inactive until the panel that holds column i, then
   //   updated over the remaining (n - c1) columns of every later panel -> rows x (n - i)^2.
   // Returns the largest per-rank load of an assignment.
+  double block_weight(long long b) const {
+    const double pos = ((double)b + 0.5) * (double)db;
+    double wgt;
+    if (grad && pos > (double)(n + c)) {
+      const double rest = std::max(0.0, (double)n - (pos - (double)(n + c)));
+      wgt = rest * rest;
+    } else {
+      wgt = std::min(pos, (double)n) * std::min(pos, (double)n);
+    }
+    return (double)block_rows(b) * wgt;
+  }
   double max_load(int shift) const {
     std::vector<double> w((size_t)P, 0.0);
-    for (long long b = 0; b < nblocks; b++) {
-      const int r = shift < 0 ? (int)(b % P) : snake_owner(b, shift);
-      const double pos = ((double)b + 0.5) * (double)db;
-      double wgt;
-      if (grad && pos > (double)(n + c)) {
-        const double rest = std::max(0.0, (double)n - (pos - (double)(n + c)));
-        wgt = rest * rest;
-      } else {
-        wgt = std::min(pos, (double)n) * std::min(pos, (double)n);
-      }
-      w[r] += (double)block_rows(b) * wgt;
-    }
+    for (long long b = 0; b < nblocks; b++) w[shift < 0 ? (int)(b % P) : snake_owner(b, shift)] += block_weight(b);
     return *std::max_element(w.begin(), w.end());
   }
   bool build_layout() {
@@ -584,7 +584,7 @@ int smnngp_mg_create_predict(smnngp_mg** out, int rank, int world, int64_t n, in
 
 // Pure host function (no CUDA call): the block -> rank map a handle with these parameters would use.
 // layout: 0 cyclic, 1 snake, 2 snake_end, 3 auto.  owner_out [nblocks]; returns nblocks (< 0: invalid argument).
-// load_out [world] (optional): modelled update work per rank (rows x position^2 per block), for tests / diagnostics.
+// load_out [world] (optional): modelled update work per rank (the model the "auto" map minimises), for tests / diagnostics.
 int64_t smnngp_mg_layout(int world, int64_t n, int64_t extra_rows, int64_t block, int layout, int* owner_out,
                          double* load_out) {
   if (world < 1 || world > MAX_PEERS || n <= 0 || extra_rows < 0 || block <= 0 || layout < 0 || layout > 3) return -1;
@@ -601,10 +601,7 @@ int64_t smnngp_mg_layout(int world, int64_t n, int64_t extra_rows, int64_t block
     for (long long b = 0; b < g.nblocks; b++) owner_out[b] = g.owner_tab[b];
   if (load_out) {
     for (int r = 0; r < world; r++) load_out[r] = 0.0;
-    for (long long b = 0; b < g.nblocks; b++) {
-      const double pos = ((double)b + 0.5) * (double)g.db;
-      load_out[g.owner_tab[b]] += (double)g.block_rows(b) * pos * pos;
-    }
+    for (long long b = 0; b < g.nblocks; b++) load_out[g.owner_tab[b]] += g.block_weight(b);
   }
   return g.nblocks;
 }

@@ -265,3 +265,37 @@ def test_stream_watchdog_releases_waits_and_poisons_info():
     assert not dog.fired and int(info.item()) == 0 and int(flags.abs().sum()) == 0
     dog.watch(Ev(False), info, 1234, poll_s=0.02).join(timeout=5)
     assert dog.fired and int(info.item()) == 0x7fffffff and bool((flags >= 1234 + (1 << 40)).all())
+
+
+def test_c_driver_block_layouts_property():
+    """property test (hypothesis) of the host-side layout function over random group sizes / orders / block sizes: every
+    map is a partition with one block per rank per cycle in the alternating form, and `auto` is never worse than the
+    other maps under the load model"""
+    import ctypes as C
+    from hypothesis import given, settings, strategies as st
+    import smnngp_b200 as sm
+    lib = sm._lib.load()
+
+    @settings(max_examples=60, deadline=None)
+    @given(world=st.integers(1, 8), n=st.integers(1, 40000), block=st.sampled_from([128, 256, 384, 512]),
+           extra=st.integers(0, 700))
+    def check(world, n, block, extra):
+        nb = -(-(n + extra) // block)
+        worst = {}
+        for layout in (0, 1, 2, 3):
+            owner = (C.c_int * nb)()
+            load = (C.c_double * world)()
+            assert lib.smnngp_mg_layout(world, n, extra, block, layout, owner, load) == nb
+            owner = list(owner)
+            for r in range(world):
+                mine = [b for b in range(nb) if owner[b] == r]
+                if len(mine) > 1:
+                    even, odd = mine[0], mine[1] - world
+                    assert all(b == lb * world + (odd if lb & 1 else even) for lb, b in enumerate(mine))
+            # every window of `world` consecutive blocks that is aligned to a cycle of the map holds each rank at most
+            # twice (snake turn-around) and the union over all blocks is a partition by construction
+            assert all(0 <= o < world for o in owner)
+            worst[layout] = max(load)
+        assert worst[3] <= min(worst[0], worst[1], worst[2]) * (1 + 1e-12)
+
+    check()
