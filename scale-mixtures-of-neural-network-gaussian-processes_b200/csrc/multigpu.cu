@@ -154,7 +154,9 @@ struct smnngp_mg {
     snake_shift = -1;
     if (layout == 1) snake_shift = 0;
     if (layout == 2) snake_shift = (int)((2 * P - nblocks % (2 * P)) % (2 * P));
-    if (layout == 3) {
+    // two ranks: plain cyclic measured faster than any snake (1174 vs 1189 ms at C3 on one box, 1185 ms for the phase
+    // the model prefers) - the model's spread is < 1 % there and the snake's two-in-a-row ownership costs more
+    if (layout == 3 && P > 2) {
       double best = max_load(-1);
       for (int sft = 0; sft < 2 * P; sft++) {
         const double m = max_load(sft);

@@ -241,7 +241,10 @@ def test_c_driver_block_layouts(world, n, block):
             # one block per cycle of `world` consecutive blocks (so local block index = position in the list)
             assert all(mine[i + 1] - mine[i] < 2 * world for i in range(len(mine) - 1))
         res[layout] = max(load) / (sum(load) / world)
-    assert res[3] <= res[0] + 1e-12 and res[3] <= res[1] + 1e-12 and res[3] <= res[2] + 1e-12
+    if world > 2:
+        assert res[3] <= res[0] + 1e-12 and res[3] <= res[1] + 1e-12 and res[3] <= res[2] + 1e-12
+    else:
+        assert res[3] == res[0]                    # two ranks: auto = plain cyclic (measured faster)
     if world == 8 and n == 60000:
         assert res[0] > 1.08 and res[3] < 1.03          # 8.6 % -> 2.5 % over the mean (profiles/r02_layouts_8gpu.txt)
 
@@ -296,6 +299,9 @@ def test_c_driver_block_layouts_property():
             # twice (snake turn-around) and the union over all blocks is a partition by construction
             assert all(0 <= o < world for o in owner)
             worst[layout] = max(load)
-        assert worst[3] <= min(worst[0], worst[1], worst[2]) * (1 + 1e-12)
+        if world > 2:
+            assert worst[3] <= min(worst[0], worst[1], worst[2]) * (1 + 1e-12)
+        else:
+            assert worst[3] == worst[0]
 
     check()
